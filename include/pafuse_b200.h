@@ -1,0 +1,134 @@
+/*
+ * pafuse_b200 -- C ABI of the B200-native PAFUSE denoising inference path.
+ *
+ * The reference (valeoai/PAFUSE) is pure PyTorch and has no FFI; the boundary this
+ * library replaces is the eval branch of the nn.Module contract of `D3DP` /
+ * `MixSTE2` plus three free functions.  Each entry point cites the reference
+ * interface it stands in for (paths relative to the reference root).  The Python
+ * host module `pafuse_b200/diffusionpose.py` binds these symbols with ctypes and
+ * keeps the reference's constructor / forward signatures.
+ *
+ * Conventions
+ *   - plain C types only; all tensor arguments are DEVICE pointers to contiguous
+ *     fp32 data unless stated otherwise; the caller owns them.
+ *   - every call enqueues work on the caller's CUDA stream (`stream` is a
+ *     cudaStream_t passed as void*) and returns without synchronising.
+ *   - return value: 0 = ok, negative = error (PAFUSE_E_*); `pafuse_last_error()`
+ *     returns a thread-local description.  Nothing throws across the ABI.
+ *   - a context is bound to the device current at `pafuse_create` and is not
+ *     thread-safe.  There is no CPU fallback: without a CUDA device every compute
+ *     entry point fails with PAFUSE_E_CUDA.
+ */
+#ifndef PAFUSE_B200_H
+#define PAFUSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAFUSE_MAX_PARTS 4
+#define PAFUSE_E_ARG (-1)
+#define PAFUSE_E_CUDA (-2)
+#define PAFUSE_E_STATE (-3)
+
+typedef struct pafuse_ctx pafuse_ctx;
+
+/* Static description of the part-based denoiser.  Mirrors what D3DP.__init__ derives
+ * from `args` and `dataset` (common/diffusionpose.py:59-153): frames, num_kps,
+ * depth (args.model.dep), heads (8), the part table {body,face,hands} with its
+ * channel widths (:141) and joint-index lists (:72-83), the flip-TTA joint
+ * permutation built from joints_left/right (:197-198) and args.ft2d.scale. */
+typedef struct pafuse_config {
+    int32_t frames;                              /* F, args.model.number_of_frames (27) */
+    int32_t num_kps;                             /* args.data.num_kps (134) */
+    int32_t depth;                               /* args.model.dep (8) */
+    int32_t heads;                               /* 8 */
+    int32_t num_parts;                           /* 3 */
+    int32_t part_channels[PAFUSE_MAX_PARTS];     /* 384 / 224 / 256 */
+    int32_t part_num_joints[PAFUSE_MAX_PARTS];   /* 24 / 68 / 42 */
+    const int32_t* part_joints[PAFUSE_MAX_PARTS];/* host arrays: whole-body joint ids, concat order */
+    const int32_t* flip_perm;                    /* host array [num_kps]: source joint under L/R swap */
+    float scale;                                 /* args.ft2d.scale */
+    int32_t max_seqs;                            /* sequences (clip x hypothesis x {orig,flip}) per workspace pass */
+} pafuse_config;
+
+const char* pafuse_last_error(void);
+const char* pafuse_version(void);
+
+/* Number of CUDA kernels this library has launched on the calling thread (bench.py's gpu_launches). */
+int64_t pafuse_launch_count(void);
+
+int pafuse_create(const pafuse_config* cfg, pafuse_ctx** out);
+void pafuse_destroy(pafuse_ctx* ctx);
+
+/* Weights: replaces nn.Module.load_state_dict for `pose_estimator.<part>.<name>`
+ * (keys/shapes of common/mixste.py:141-210).  `name` is the sub-key after the part,
+ * e.g. "STEblocks.3.attn.qkv.weight"; `data` is fp32, host or device (`on_device`).
+ * Unknown names return PAFUSE_E_ARG.  Call pafuse_commit_weights once all tensors
+ * are set: it derives the bf16 hi/lo operand copies the tensor-core GEMMs read. */
+int pafuse_set_weight(pafuse_ctx* ctx, int32_t part, const char* name, const float* data, int64_t numel,
+                      int32_t on_device);
+int pafuse_commit_weights(pafuse_ctx* ctx, void* stream);
+
+/* pred_parts: D3DP.pred_parts + split_data (common/diffusionpose.py:163-172,328-335)
+ * = MixSTE2.forward per part (common/mixste.py:278-298), results concatenated on the
+ * joint axis.  x2d [B,F,num_kps,2], x3d [B,H,F,num_kps,3] (already clamped/scaled
+ * x_t), sinus = concatenated sinusoidal timestep embeddings of the parts
+ * (mixste.py:132-139; sum(part_channels) floats, device) -> out [B,H,F,num_kps,3]. */
+int pafuse_pred_parts(pafuse_ctx* ctx, const float* x2d, const float* x3d, const float* sinus, float* out, int32_t B,
+                      int32_t H, void* stream);
+
+/* One DDIM step: D3DP.model_predictions_fliping (flip != 0, diffusionpose.py:192-225)
+ * or model_predictions (flip == 0, :174-190) followed by the state update of
+ * ddim_sample[_flip] (:298-312).
+ *   img      [B,H,F,num_kps,3]  sampler state, updated in place
+ *   noise    [B,H,F,num_kps,3]  the randn_like draw of this step (ignored when last != 0)
+ *   x0_out   base pointer of preds_all[:, k]; clip b is written at x0_out + b*x0_batch_stride
+ *   sqrt_recip, sqrt_recipm1    fp64 buffers at t (:119-120); sqrt_an, c, sigma: fp32 casts of the
+ *   fp64 scalars of :302-306 (c64 = the fp64 value of c, used by the non-flip sampler)        */
+int pafuse_ddim_step(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, const float* sinus, float* img,
+                     const float* noise, float* x0_out, int64_t x0_batch_stride, int32_t B, int32_t H, int32_t flip,
+                     int32_t last, double sqrt_recip, double sqrt_recipm1, double c64, float sqrt_an, float c,
+                     float sigma, void* stream);
+
+/* wb_pose_from_parts (common/utils.py:113-126): pose [poses,num_kps,3] -> out.
+ * conn_of_joint: host array [num_kps], connection joint of the part each joint belongs to
+ * (body -> 0, face -> 1, left hand -> 10, right hand -> 11; -1 = untouched/zero).
+ * mutate_input != 0 reproduces the reference's in-place negation of the connection rows of `pose`. */
+int pafuse_wb_pose_from_parts(pafuse_ctx* ctx, float* pose, float* out, const int32_t* conn_of_joint, int64_t poses,
+                              int32_t mutate_input, void* stream);
+
+/* project_to_2d (common/camera.py:30-60): X [n_cams, pts_per_cam, 3], cam [n_cams,9] -> out [.,.,2]. */
+int pafuse_project_to_2d(pafuse_ctx* ctx, const float* X, const float* cam, float* out, int64_t n_cams,
+                         int64_t pts_per_cam, void* stream);
+
+/* Multi-hypothesis aggregation: reprojection (main_h3wb.py:336-342), J-Agg select
+ * (common/loss.py:101-108, pose form common/visualization.py:453-463) and P-Agg mean
+ * (loss.py:68-70).  pred [B,K,H,F,J,3] whole-body, traj [B,F,1,3] or NULL, cam [1,9]
+ * (cam_per_clip == 0) or [B,9], x2d [B,F,J,2] -> jagg,pagg [B,K,F,J,3]; select [B,K,F,J] int32
+ * and reproj [B,K,H,F,J,2] are optional (NULL to skip). */
+int pafuse_aggregate(pafuse_ctx* ctx, const float* pred, const float* traj, const float* cam, int32_t cam_per_clip,
+                     const float* x2d, float* jagg, float* pagg, int32_t* select, float* reproj, int32_t B, int32_t K,
+                     int32_t H, void* stream);
+
+/* ---- unit-level entry points (tests and profiling; same kernels the path uses) ---- */
+
+/* y = x W^T + b through the tcgen05 bf16x3 GEMM (use_simt != 0: CUDA-core debug reference).
+ * x [M,K] fp32, w [N,K] fp32, b [N]; epilogue 0: y fp32 [M,N]; 1: y = gelu(.) returned as fp32
+ * (hi+lo recombined); 2: y += x W^T + b in place. */
+int pafuse_linear(pafuse_ctx* ctx, const float* x, const float* w, const float* b, float* y, int64_t M, int32_t N,
+                  int32_t K, int32_t epilogue, int32_t use_simt, void* stream);
+
+/* softmax(q k^T / sqrt(hd)) v on qkv [S*F*J, 3C] -> out fp32 [S*F*J, C]; temporal selects the axis. */
+int pafuse_attention(pafuse_ctx* ctx, const float* qkv, float* out, int32_t S, int32_t J, int32_t C, int32_t temporal,
+                     void* stream);
+
+/* debugging switch: route the path's GEMMs through the CUDA-core reference kernel */
+int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAFUSE_B200_H */

@@ -1,0 +1,243 @@
+"""ctypes binding of the C-ABI library (``include/pafuse_b200.h``).
+
+PyTorch is used only for device memory and streams: every call passes raw
+``data_ptr()`` values and the current CUDA stream handle.  There is no CPU or
+PyTorch fallback: if the shared library is missing or no sm_100 device is
+present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
+
+import torch
+
+from . import build as _build
+
+MAX_PARTS = 4
+
+
+class PafuseConfig(ctypes.Structure):
+    _fields_ = [
+        ("frames", c_int32), ("num_kps", c_int32), ("depth", c_int32), ("heads", c_int32), ("num_parts", c_int32),
+        ("part_channels", c_int32 * MAX_PARTS), ("part_num_joints", c_int32 * MAX_PARTS),
+        ("part_joints", POINTER(c_int32) * MAX_PARTS), ("flip_perm", POINTER(c_int32)),
+        ("scale", c_float), ("max_seqs", c_int32),
+    ]
+
+
+_SIGNATURES = {
+    "pafuse_last_error": (c_char_p, []),
+    "pafuse_version": (c_char_p, []),
+    "pafuse_launch_count": (c_int64, []),
+    "pafuse_create": (c_int32, [POINTER(PafuseConfig), POINTER(c_void_p)]),
+    "pafuse_destroy": (None, [c_void_p]),
+    "pafuse_set_weight": (c_int32, [c_void_p, c_int32, c_char_p, c_void_p, c_int64, c_int32]),
+    "pafuse_commit_weights": (c_int32, [c_void_p, c_void_p]),
+    "pafuse_pred_parts": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "pafuse_ddim_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_int32, c_int32, c_int32, c_int32, c_double, c_double, c_double, c_float, c_float,
+                                   c_float, c_void_p]),
+    "pafuse_wb_pose_from_parts": (c_int32, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_int64, c_int32, c_void_p]),
+    "pafuse_project_to_2d": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "pafuse_aggregate": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "pafuse_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                c_int32, c_void_p]),
+    "pafuse_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "pafuse_set_debug_simt_gemm": (c_int32, [c_void_p, c_int32]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen the in-tree library (building it first when sources are newer and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on the box and a stale/missing .so
+            if not os.path.isfile(path):
+                raise RuntimeError(f"pafuse_b200: native library missing and cannot be built: {e}") from e
+    if not os.path.isfile(path):
+        raise RuntimeError(f"pafuse_b200: native library not found at {path}; run `python -m pafuse_b200.build`")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class PafuseError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().pafuse_last_error().decode(errors="replace")
+        raise PafuseError(f"{what} failed (rc={rc}): {msg}")
+
+
+def _ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, device=None):
+    t = t.detach()
+    if device is not None and t.device != device:
+        t = t.to(device)
+    return t.to(torch.float32).contiguous()
+
+
+class NativeContext:
+    """Owns one ``pafuse_ctx`` bound to one CUDA device."""
+
+    def __init__(self, frames, num_kps, depth, heads, part_channels, part_joints, flip_perm, scale, max_seqs, device):
+        if not torch.cuda.is_available():
+            raise PafuseError("pafuse_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device(device)
+        self.num_kps = num_kps
+        self.frames = frames
+        self.part_channels = list(part_channels)
+        cfg = PafuseConfig()
+        cfg.frames, cfg.num_kps, cfg.depth, cfg.heads, cfg.num_parts = frames, num_kps, depth, heads, len(part_channels)
+        self._keep = []
+        for i, (C, joints) in enumerate(zip(part_channels, part_joints)):
+            arr = (c_int32 * len(joints))(*joints)
+            self._keep.append(arr)
+            cfg.part_channels[i] = C
+            cfg.part_num_joints[i] = len(joints)
+            cfg.part_joints[i] = ctypes.cast(arr, POINTER(c_int32))
+        fp = (c_int32 * num_kps)(*flip_perm)
+        self._keep.append(fp)
+        cfg.flip_perm = ctypes.cast(fp, POINTER(c_int32))
+        cfg.scale = float(scale)
+        cfg.max_seqs = int(max_seqs)
+        handle = c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_create(ctypes.byref(cfg), ctypes.byref(handle)), "pafuse_create")
+        self.handle = handle
+
+    def close(self):
+        if getattr(self, "handle", None):
+            with torch.cuda.device(self.device):
+                self.lib.pafuse_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights
+    def set_weight(self, part: int, name: str, tensor):
+        t = _f32c(tensor)
+        on_dev = 1 if t.is_cuda else 0
+        if t.is_cuda and t.device != self.device:
+            t = t.to(self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_set_weight(self.handle, part, name.encode(), _ptr(t), t.numel(), on_dev),
+                  f"pafuse_set_weight({name})")
+
+    def commit_weights(self):
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_commit_weights(self.handle, _stream()), "pafuse_commit_weights")
+
+    # ---- compute
+    def pred_parts(self, x2d, x3d, sinus, out=None):
+        B, H = x3d.shape[0], x3d.shape[1]
+        x2d, x3d, sinus = _f32c(x2d, self.device), _f32c(x3d, self.device), _f32c(sinus, self.device)
+        if out is None:
+            out = torch.empty_like(x3d)
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_pred_parts(self.handle, _ptr(x2d), _ptr(x3d), _ptr(sinus), _ptr(out), B, H, _stream()),
+                  "pafuse_pred_parts")
+        return out
+
+    def ddim_step(self, x2d, x2d_flip, sinus, img, noise, x0_out, x0_batch_stride, B, H, flip, last,
+                  sqrt_recip, sqrt_recipm1, c64, sqrt_an, c, sigma):
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_ddim_step(self.handle, _ptr(x2d), _ptr(x2d_flip), _ptr(sinus), _ptr(img), _ptr(noise),
+                                            c_void_p(x0_out), x0_batch_stride, B, H, int(flip), int(last),
+                                            sqrt_recip, sqrt_recipm1, c64, sqrt_an, c, sigma, _stream()),
+                  "pafuse_ddim_step")
+
+    def wb_pose_from_parts(self, pose, conn_of_joint, mutate_input=True):
+        assert pose.is_cuda and pose.dtype == torch.float32 and pose.is_contiguous()
+        out = torch.empty_like(pose)
+        poses = pose.numel() // (self.num_kps * 3)
+        arr = (c_int32 * self.num_kps)(*conn_of_joint)
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_wb_pose_from_parts(self.handle, _ptr(pose), _ptr(out), arr, poses,
+                                                     1 if mutate_input else 0, _stream()), "pafuse_wb_pose_from_parts")
+        return out
+
+    def project_to_2d(self, X, cam):
+        X, cam = _f32c(X, self.device), _f32c(cam, self.device)
+        n_cams = X.shape[0]
+        pts = X.numel() // (3 * n_cams)
+        out = torch.empty(tuple(X.shape[:-1]) + (2,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_project_to_2d(self.handle, _ptr(X), _ptr(cam), _ptr(out), n_cams, pts, _stream()),
+                  "pafuse_project_to_2d")
+        return out
+
+    def aggregate(self, pred, traj, cam, x2d, want_select=True, want_reproj=False):
+        pred, x2d, cam = _f32c(pred, self.device), _f32c(x2d, self.device), _f32c(cam, self.device)
+        traj = None if traj is None else _f32c(traj, self.device)
+        B, K, H, F, J, _ = pred.shape
+        jagg = torch.empty((B, K, F, J, 3), dtype=torch.float32, device=self.device)
+        pagg = torch.empty_like(jagg)
+        sel = torch.empty((B, K, F, J), dtype=torch.int32, device=self.device) if want_select else None
+        rep = torch.empty((B, K, H, F, J, 2), dtype=torch.float32, device=self.device) if want_reproj else None
+        cam_per_clip = 1 if (cam.dim() == 2 and cam.shape[0] == B and B > 1) else 0
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_aggregate(self.handle, _ptr(pred), _ptr(traj), _ptr(cam), cam_per_clip, _ptr(x2d),
+                                            _ptr(jagg), _ptr(pagg), _ptr(sel), _ptr(rep), B, K, H, _stream()),
+                  "pafuse_aggregate")
+        return jagg, pagg, sel, rep
+
+    # ---- unit-level
+    def linear(self, x, w, b, epilogue=0, use_simt=False, y=None):
+        x, w, b = _f32c(x, self.device), _f32c(w, self.device), _f32c(b, self.device)
+        M, K = x.shape
+        N = w.shape[0]
+        if y is None:
+            y = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_linear(self.handle, _ptr(x), _ptr(w), _ptr(b), _ptr(y), M, N, K, epilogue,
+                                         1 if use_simt else 0, _stream()), "pafuse_linear")
+        return y
+
+    def attention(self, qkv, S, J, C, temporal):
+        qkv = _f32c(qkv, self.device)
+        out = torch.empty((qkv.shape[0], C), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_attention(self.handle, _ptr(qkv), _ptr(out), S, J, C, 1 if temporal else 0, _stream()),
+                  "pafuse_attention")
+        return out
+
+    def set_debug_simt_gemm(self, enable: bool):
+        check(self.lib.pafuse_set_debug_simt_gemm(self.handle, 1 if enable else 0), "pafuse_set_debug_simt_gemm")
+
+    def launch_count(self) -> int:
+        return int(self.lib.pafuse_launch_count())

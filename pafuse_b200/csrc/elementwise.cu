@@ -1,0 +1,513 @@
+// HBM-bound kernels of the denoising path: embedding, time-MLP, LayerNorm(+split),
+// head, DDIM x0/eps update, part re-assembly and multi-hypothesis aggregation.
+//
+// Activation layout everywhere: token row m = (s*F + f)*J + j of a [S,F,J,C] tensor
+// (s = sequence = clip x hypothesis x {orig,flip}); no transposes between spatial
+// and temporal blocks (replaces the 16 rearrange copies of mixste.py:244-274).
+#include "kernels.cuh"
+
+namespace pafuse {
+
+// ------------------------------------------------------------------ weight split
+__global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                     __nv_bfloat16* __restrict__ lo, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        __nv_bfloat16 h, l;
+        split_bf16(w[i], h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+int launch_split_weights(const float* w, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    split_weights_kernel<<<blocks, 256, 0, st>>>(w, hi, lo, n);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ time MLP
+// temb = W2 * gelu(W1 * sinus + b1) + b2      (mixste.py:179-184); one CTA per part-call.
+__global__ void time_mlp_kernel(const float* __restrict__ sinus, const float* __restrict__ w1,
+                                const float* __restrict__ b1, const float* __restrict__ w2,
+                                const float* __restrict__ b2, float* __restrict__ temb, int C) {
+    extern __shared__ float sm[];
+    float* e = sm;           // [C]
+    float* h = sm + C;       // [2C]
+    for (int i = threadIdx.x; i < C; i += blockDim.x) e[i] = sinus[i];
+    __syncthreads();
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int o = warp; o < 2 * C; o += nw) {
+        const float* wr = w1 + (size_t)o * C;
+        float acc = 0.f;
+        for (int i = lane; i < C; i += 32) acc = fmaf(wr[i], e[i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) h[o] = gelu_erf(acc + b1[o]);
+    }
+    __syncthreads();
+    for (int o = warp; o < C; o += nw) {
+        const float* wr = w2 + (size_t)o * 2 * C;
+        float acc = 0.f;
+        for (int i = lane; i < 2 * C; i += 32) acc = fmaf(wr[i], h[i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) temb[o] = acc + b2[o];
+    }
+}
+
+int launch_time_mlp(const float* sinus, const float* w1, const float* b1, const float* w2, const float* b2,
+                    float* temb, int C, cudaStream_t st) {
+    time_mlp_kernel<<<1, 512, 3 * C * sizeof(float), st>>>(sinus, w1, b1, w2, b2, temb, C);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ embedding
+// x[m,:] = We * [u,v,x,y,z] + be + Spatial_pos_embed[j] + temb    (mixste.py:227-235)
+// The 3D input is taken from the sampler state `img` (clamped/scaled when
+// apply_clamp, diffusionpose.py:193-194) and, for flip sequences (s >= R_flip_start),
+// x is negated and left/right joints are swapped on the fly (:195-198).
+// One warp per token row; lanes stride over channels.
+__global__ void embed_kernel(EmbedParams p) {
+    int warps_per_block = blockDim.x >> 5;
+    long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (m >= p.M) return;
+    int lane = threadIdx.x & 31;
+    int j = (int)(m % p.J);
+    long long sf = m / p.J;
+    int f = (int)(sf % p.F);
+    int s = (int)(sf / p.F) + p.s0;               // global sequence id
+    bool flip = s >= p.R;                          // second half of the sequence set = flip-TTA twins
+    int r = flip ? s - p.R : s;                    // (clip, hypothesis) id
+    int b = r / p.H;
+    int g = p.part_joints[j];                      // whole-body joint id
+    int gsrc = flip ? p.flip_perm[g] : g;
+    const float* x2 = (flip ? p.x2d_flip : p.x2d) + (((size_t)b * p.F + f) * p.num_kps + g) * 2;
+    const float* x3 = p.x3d + (((size_t)r * p.F + f) * p.num_kps + gsrc) * 3;
+    float in[5];
+    in[0] = x2[0];
+    in[1] = x2[1];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float v = x3[c];
+        if (p.apply_clamp) {
+            v = fminf(fmaxf(v, -p.clamp), p.clamp);
+            v = __fdiv_rn(v, p.scale);
+        }
+        in[2 + c] = v;
+    }
+    if (flip) in[2] = -in[2];
+    float* xo = p.x + (size_t)m * p.C;
+    const float* pos = p.spos + (size_t)j * p.C;
+    for (int c = lane; c < p.C; c += 32) {
+        const float* w = p.we + c * 5;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) acc = fmaf(in[i], w[i], acc);
+        acc += p.be[c];
+        acc += pos[c];
+        acc += p.temb[c];
+        xo[c] = acc;
+    }
+}
+
+int launch_embed(const EmbedParams& p, cudaStream_t st) {
+    if (p.M == 0) return 0;
+    const int wpb = 8;
+    long long blocks = (p.M + wpb - 1) / wpb;
+    embed_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(p);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ LayerNorm (+ chained norm) + bf16 split
+// Optional first stage (g0 != nullptr):  x <- LN(x; g0,b0,eps0) [+ add_f[f,:]]   written back (residual stream)
+//     = the shared Spatial_norm / Temporal_norm after every block (mixste.py:243,257,269,273)
+//       and the Temporal_pos_embed add before TTE block 0 (:250).
+// Second stage (g1 != nullptr):         a  = LN(x; g1,b1,eps1) -> bf16 hi/lo     (norm1 / norm2 of the next GEMM)
+// One warp per row, row kept in registers (C <= 32*MAXV).
+template <int MAXV>
+__global__ void ln_chain_kernel(LnParams p) {
+    int warps_per_block = blockDim.x >> 5;
+    long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (m >= p.M) return;
+    int lane = threadIdx.x & 31;
+    const int C = p.C;
+    float* xr = p.x + (size_t)m * C;
+    float v[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int c = lane + 32 * i;
+        v[i] = c < C ? xr[c] : 0.f;
+    }
+    const float invC = 1.0f / (float)C;
+    if (p.g0) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) s += v[i];
+        float mean = warp_sum(s) * invC;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            int c = lane + 32 * i;
+            float d = c < C ? v[i] - mean : 0.f;
+            q += d * d;
+        }
+        float rstd = (1.0f / sqrtf(warp_sum(q) * invC + p.eps0));
+        const float* addr = nullptr;
+        if (p.add_f) {
+            int f = (int)((m / p.J) % p.F);
+            addr = p.add_f + (size_t)f * C;
+        }
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            int c = lane + 32 * i;
+            if (c < C) {
+                float y = (v[i] - mean) * rstd * p.g0[c] + p.b0[c];
+                if (addr) y += addr[c];
+                v[i] = y;
+                xr[c] = y;
+            }
+        }
+    }
+    if (p.g1) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) s += v[i];
+        float mean = warp_sum(s) * invC;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            int c = lane + 32 * i;
+            float d = c < C ? v[i] - mean : 0.f;
+            q += d * d;
+        }
+        float rstd = (1.0f / sqrtf(warp_sum(q) * invC + p.eps1));
+        __nv_bfloat16* oh = p.out_hi + (size_t)m * C;
+        __nv_bfloat16* ol = p.out_lo + (size_t)m * C;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            int c = lane + 32 * i;
+            if (c < C) {
+                float y = (v[i] - mean) * rstd * p.g1[c] + p.b1[c];
+                __nv_bfloat16 h, l;
+                split_bf16(y, h, l);
+                oh[c] = h;
+                ol[c] = l;
+            }
+        }
+    }
+}
+
+int launch_ln_chain(const LnParams& p, cudaStream_t st) {
+    if (p.M == 0) return 0;
+    const int wpb = 8;
+    unsigned blocks = (unsigned)((p.M + wpb - 1) / wpb);
+    if (p.C <= 256)
+        ln_chain_kernel<8><<<blocks, wpb * 32, 0, st>>>(p);
+    else if (p.C <= 384)
+        ln_chain_kernel<12><<<blocks, wpb * 32, 0, st>>>(p);
+    else {
+        set_last_error("ln_chain: C=%d > 384 unsupported", p.C);
+        return -1;
+    }
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ head
+// y = Linear(C,3)( LN_head( LN_shared(x) ) )      (mixste.py:273, :207-210, :291)
+// written straight into the whole-body prediction tensor [S,F,num_kps,3] at the
+// part's joint ids (replaces torch.cat, diffusionpose.py:165-171).
+template <int MAXV>
+__global__ void head_kernel(HeadParams p) {
+    int warps_per_block = blockDim.x >> 5;
+    long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (m >= p.M) return;
+    int lane = threadIdx.x & 31;
+    const int C = p.C;
+    const float* xr = p.x + (size_t)m * C;
+    float v[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int c = lane + 32 * i;
+        v[i] = c < C ? xr[c] : 0.f;
+    }
+    const float invC = 1.0f / (float)C;
+#pragma unroll
+    for (int stage = 0; stage < 2; ++stage) {
+        const float* g = stage == 0 ? p.g0 : p.g1;
+        const float* bb = stage == 0 ? p.b0 : p.b1;
+        float eps = stage == 0 ? p.eps0 : p.eps1;
+        if (!g) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) s += v[i];
+        float mean = warp_sum(s) * invC;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            int c = lane + 32 * i;
+            float d = c < C ? v[i] - mean : 0.f;
+            q += d * d;
+        }
+        float rstd = (1.0f / sqrtf(warp_sum(q) * invC + eps));
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            int c = lane + 32 * i;
+            if (c < C) v[i] = (v[i] - mean) * rstd * g[c] + bb[c];
+        }
+    }
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int c = lane + 32 * i;
+        if (c < C) {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) acc[o] = fmaf(v[i], p.wh[o * C + c], acc[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o) acc[o] = warp_sum(acc[o]);
+    if (lane < 3) {
+        int j = (int)(m % p.J);
+        long long sf = m / p.J + (long long)p.s0 * p.F;     // global (s*F + f)
+        int g = p.part_joints[j];
+        float y = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : acc[2]) + p.bh[lane];
+        p.pred[((size_t)sf * p.num_kps + g) * 3 + lane] = y;
+    }
+}
+
+int launch_head(const HeadParams& p, cudaStream_t st) {
+    if (p.M == 0) return 0;
+    const int wpb = 8;
+    unsigned blocks = (unsigned)((p.M + wpb - 1) / wpb);
+    if (p.C <= 256)
+        head_kernel<8><<<blocks, wpb * 32, 0, st>>>(p);
+    else if (p.C <= 384)
+        head_kernel<12><<<blocks, wpb * 32, 0, st>>>(p);
+    else {
+        set_last_error("head: C=%d > 384 unsupported", p.C);
+        return -1;
+    }
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ DDIM step (x0 / eps / update)
+// diffusionpose.py:211-225 (un-flip, average, scale, clamp, x0->eps in fp64) and
+// :302-312 (img update, fp32, separate mul/add roundings like eager PyTorch).
+// One thread per (r, f, joint); the three coordinates are handled together.
+__global__ void ddim_step_kernel(DdimParams p) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)p.R * p.F * p.num_kps;
+    if (idx >= total) return;
+    int g = (int)(idx % p.num_kps);
+    long long rf = idx / p.num_kps;                 // r*F + f
+    int f = (int)(rf % p.F);
+    long long r = rf / p.F;
+    long long b = r / p.H;
+    int h = (int)(r % p.H);
+    const float* po = p.pred + (size_t)idx * 3;
+    float x0v[3];
+    if (p.flip) {
+        const float* pf = p.pred + ((size_t)((long long)p.R * p.F + rf) * p.num_kps + p.flip_perm[g]) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a = po[c];
+            float bflip = c == 0 ? -pf[c] : pf[c];
+            x0v[c] = __fdiv_rn(__fadd_rn(a, bflip), 2.0f);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x0v[c] = po[c];
+    }
+    float* x0o = p.x0_out + (size_t)b * p.x0_batch_stride + (((size_t)h * p.F + f) * p.num_kps + g) * 3;
+    float* img = p.img + (size_t)idx * 3;
+    const float* nz = p.noise ? p.noise + (size_t)idx * 3 : nullptr;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float x0 = __fmul_rn(x0v[c], p.scale);
+        x0 = fminf(fmaxf(x0, -p.clamp), p.clamp);
+        x0o[c] = x0;
+        if (p.last) {
+            img[c] = x0;
+        } else {
+            double e64 = __ddiv_rn(__dsub_rn(__dmul_rn(p.sqrt_recip, (double)img[c]), (double)x0), p.sqrt_recipm1);
+            if (p.flip) {
+                float eps = (float)e64;
+                img[c] = __fadd_rn(__fadd_rn(__fmul_rn(x0, p.sqrt_an), __fmul_rn(p.c, eps)), __fmul_rn(p.sigma, nz[c]));
+            } else {
+                // non-TTA sampler keeps eps in fp64 and casts the sum (diffusionpose.py:189, :265-268)
+                double t1 = (double)__fmul_rn(x0, p.sqrt_an);
+                double t2 = __dmul_rn(p.c64, e64);
+                double t3 = (double)__fmul_rn(p.sigma, nz[c]);
+                img[c] = (float)__dadd_rn(__dadd_rn(t1, t2), t3);
+            }
+        }
+    }
+}
+
+int launch_ddim_step(const DdimParams& p, cudaStream_t st) {
+    long long total = (long long)p.R * p.F * p.num_kps;
+    if (total == 0) return 0;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    ddim_step_kernel<<<blocks, 256, 0, st>>>(p);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ part re-assembly
+// common/utils.py:113-126 with center_pose_at_root(revert=True) (:79-92):
+//   out[root] = (-x[root]) + x[root] = +0.0 ;  out[j] = x[j] + x[conn(part of j)]
+// The reference also negates the connection rows of its INPUT in place (offset is a
+// view); that side effect is a separate launch (negate_rows) ordered after this one.
+__global__ void reassemble_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                  const int* __restrict__ conn_of_joint, long long poses, int num_kps) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= poses * num_kps) return;
+    int g = (int)(idx % num_kps);
+    long long pose = idx / num_kps;
+    int r = conn_of_joint[g];
+    const float* x = in + (size_t)idx * 3;
+    float* oo = out + (size_t)idx * 3;
+    if (r < 0) {                      // joint belongs to no re-assembled part: stays zero (zeros_like)
+        oo[0] = oo[1] = oo[2] = 0.f;
+        return;
+    }
+    const float* xr = in + ((size_t)pose * num_kps + r) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) oo[c] = (g == r) ? __fadd_rn(-x[c], x[c]) : __fadd_rn(x[c], xr[c]);
+}
+
+int launch_reassemble(const float* in, float* out, const int* conn_of_joint, long long poses, int num_kps,
+                      cudaStream_t st) {
+    long long total = poses * num_kps;
+    if (total == 0) return 0;
+    reassemble_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, conn_of_joint, poses, num_kps);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+__global__ void negate_rows_kernel(float* __restrict__ x, const int* __restrict__ rows, int nrows, long long poses,
+                                   int num_kps) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= poses * nrows * 3) return;
+    int c = (int)(idx % 3);
+    long long t = idx / 3;
+    int r = rows[t % nrows];
+    long long pose = t / nrows;
+    float* v = x + ((size_t)pose * num_kps + r) * 3 + c;
+    *v = -*v;
+}
+
+int launch_negate_rows(float* x, const int* rows, int nrows, long long poses, int num_kps, cudaStream_t st) {
+    long long total = poses * nrows * 3;
+    if (total == 0) return 0;
+    negate_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, rows, nrows, poses, num_kps);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ projection + aggregation
+// camera.py:30-60 restated with the same operation order (all roundings explicit).
+__device__ __forceinline__ void project_point(const float X[3], const float* __restrict__ cam, float uv[2]) {
+    float xx0 = fminf(fmaxf(__fdiv_rn(X[0], X[2]), -1.f), 1.f);
+    float xx1 = fminf(fmaxf(__fdiv_rn(X[1], X[2]), -1.f), 1.f);
+    float r2 = __fadd_rn(__fmul_rn(xx0, xx0), __fmul_rn(xx1, xx1));
+    float r4 = __fmul_rn(r2, r2);
+    float r6 = __fmul_rn(r4, r2);
+    float ksum = __fadd_rn(__fadd_rn(__fmul_rn(cam[4], r2), __fmul_rn(cam[5], r4)), __fmul_rn(cam[6], r6));
+    float radial = __fadd_rn(1.f, ksum);
+    float tan = __fadd_rn(__fmul_rn(cam[7], xx0), __fmul_rn(cam[8], xx1));
+    float rt = __fadd_rn(radial, tan);
+    float x0 = __fadd_rn(__fmul_rn(xx0, rt), __fmul_rn(cam[7], r2));
+    float x1 = __fadd_rn(__fmul_rn(xx1, rt), __fmul_rn(cam[8], r2));
+    uv[0] = __fadd_rn(__fmul_rn(cam[0], x0), cam[2]);
+    uv[1] = __fadd_rn(__fmul_rn(cam[1], x1), cam[3]);
+}
+
+__global__ void project_kernel(const float* __restrict__ X, const float* __restrict__ cam, float* __restrict__ out,
+                               long long npts, long long pts_per_cam) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    float x[3] = {X[i * 3], X[i * 3 + 1], X[i * 3 + 2]};
+    float uv[2];
+    project_point(x, cam + (i / pts_per_cam) * 9, uv);
+    out[i * 2] = uv[0];
+    out[i * 2 + 1] = uv[1];
+}
+
+int launch_project(const float* X, const float* cam, float* out, long long npts, long long pts_per_cam,
+                   cudaStream_t st) {
+    if (npts == 0) return 0;
+    project_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(X, cam, out, npts, pts_per_cam);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// One thread per (b,k,f,j): loop over the H hypotheses once, keeping the running
+// sum (P-Agg, loss.py:68-70) and the first minimum of the 2D reprojection error
+// (J-Agg, loss.py:101-108 / visualization.py:453-463; reprojection main_h3wb.py:336-342).
+__global__ void aggregate_kernel(AggParams p) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)p.B * p.K * p.F * p.J;
+    if (idx >= total) return;
+    int j = (int)(idx % p.J);
+    long long t = idx / p.J;
+    int f = (int)(t % p.F);
+    t /= p.F;
+    int k = (int)(t % p.K);
+    long long b = t / p.K;
+    const float* tr = p.traj ? p.traj + ((size_t)b * p.F + f) * 3 : nullptr;
+    const float* tgt = p.x2d + (((size_t)b * p.F + f) * p.J + j) * 2;
+    const float* cam = p.cam + (p.cam_per_clip ? b * 9 : 0);
+    float best = 0.f, bx[3] = {0.f, 0.f, 0.f}, sum[3] = {0.f, 0.f, 0.f};
+    int besth = 0;
+    for (int h = 0; h < p.H; ++h) {
+        const float* x = p.pred + (((((size_t)b * p.K + k) * p.H + h) * p.F + f) * p.J + j) * 3;
+        float xv[3] = {x[0], x[1], x[2]};
+        float xa[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            xa[c] = tr ? __fadd_rn(xv[c], tr[c]) : xv[c];
+            sum[c] = h == 0 ? xv[c] : __fadd_rn(sum[c], xv[c]);
+        }
+        float uv[2];
+        project_point(xa, cam, uv);
+        float d0 = __fsub_rn(uv[0], tgt[0]), d1 = __fsub_rn(uv[1], tgt[1]);
+        float err = __fsqrt_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));
+        if (p.reproj) {
+            float* ro = p.reproj + (((((size_t)b * p.K + k) * p.H + h) * p.F + f) * p.J + j) * 2;
+            ro[0] = uv[0];
+            ro[1] = uv[1];
+        }
+        if (h == 0 || err < best) {                 // strict '<' keeps the first minimum
+            best = err;
+            besth = h;
+            bx[0] = xv[0];
+            bx[1] = xv[1];
+            bx[2] = xv[2];
+        }
+    }
+    float hf = (float)p.H;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        p.jagg[(size_t)idx * 3 + c] = bx[c];
+        p.pagg[(size_t)idx * 3 + c] = __fdiv_rn(sum[c], hf);
+    }
+    if (p.select) p.select[idx] = besth;
+}
+
+int launch_aggregate(const AggParams& p, cudaStream_t st) {
+    long long total = (long long)p.B * p.K * p.F * p.J;
+    if (total == 0) return 0;
+    aggregate_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace pafuse

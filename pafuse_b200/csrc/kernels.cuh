@@ -1,0 +1,123 @@
+// Kernel parameter blocks and host-side launch entry points shared by the .cu files.
+#pragma once
+
+#include "common.cuh"
+
+namespace pafuse {
+
+struct EmbedParams {
+    long long M;              // token rows in this chunk = Sc*F*J
+    int C, J, F, H;
+    int R;                    // number of (clip,hypothesis) rows; sequences >= R are flip twins
+    int s0;                   // first global sequence id of this chunk
+    int num_kps;
+    int apply_clamp;          // x3d is the raw sampler state: clamp(+-clamp) and divide by scale
+    float clamp, scale;
+    const float* x2d;         // [B,F,num_kps,2]
+    const float* x2d_flip;    // [B,F,num_kps,2] or null
+    const float* x3d;         // [R,F,num_kps,3]
+    const int* part_joints;   // [J] whole-body joint ids (device)
+    const int* flip_perm;     // [num_kps] (device)
+    const float *we, *be;     // [C,5], [C]
+    const float* spos;        // [J,C]
+    const float* temb;        // [C]
+    float* x;                 // [M,C] out
+};
+
+struct LnParams {
+    long long M;
+    int C, J, F;
+    float* x;                 // [M,C] in (and out when g0 != null)
+    const float *g0, *b0;     // optional shared norm written back to x
+    float eps0;
+    const float* add_f;       // optional [F,C] added after the first norm (Temporal_pos_embed)
+    const float *g1, *b1;     // optional second norm -> bf16 hi/lo
+    float eps1;
+    __nv_bfloat16 *out_hi, *out_lo;
+};
+
+struct HeadParams {
+    long long M;
+    int C, J, F;
+    int s0;
+    int num_kps;
+    const float* x;
+    const float *g0, *b0;     // shared Temporal_norm (eps0)
+    float eps0;
+    const float *g1, *b1;     // head LayerNorm (eps1 = 1e-5)
+    float eps1;
+    const float *wh, *bh;     // [3,C], [3]
+    const int* part_joints;
+    float* pred;              // [S,F,num_kps,3]
+};
+
+struct DdimParams {
+    int R, F, H, num_kps;
+    int flip, last;
+    const float* pred;        // [2R or R, F, num_kps, 3]
+    const int* flip_perm;
+    float* img;               // [R,F,num_kps,3] in/out
+    const float* noise;       // [R,F,num_kps,3] or null when last
+    float* x0_out;            // base of preds_all[:, k]
+    long long x0_batch_stride;// elements between consecutive clips in x0_out
+    float scale, clamp;
+    double sqrt_recip, sqrt_recipm1, c64;
+    float sqrt_an, c, sigma;
+};
+
+struct AggParams {
+    int B, K, H, F, J;
+    int cam_per_clip;
+    const float* pred;        // [B,K,H,F,J,3]
+    const float* traj;        // [B,F,1,3] or null
+    const float* cam;         // [1,9] or [B,9]
+    const float* x2d;         // [B,F,J,2]
+    float* jagg;              // [B,K,F,J,3]
+    float* pagg;              // [B,K,F,J,3]
+    int* select;              // [B,K,F,J] or null
+    float* reproj;            // [B,K,H,F,J,2] or null
+};
+
+struct AttnParams {
+    const float* qkv;         // [M,3C]
+    __nv_bfloat16 *out_hi, *out_lo;  // [M,C]
+    int S, F, J, C;
+    int temporal;             // 0: attend over J inside (s,f); 1: over F inside (s,j)
+    float scale;              // head_dim^-0.5, set by launch_attention
+};
+
+enum GemmEpilogue { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_RESID = 2 };
+
+struct GemmArgs {
+    const __nv_bfloat16 *a_hi, *a_lo;   // [M,K]
+    const __nv_bfloat16 *w_hi, *w_lo;   // [N,K]
+    const float* bias;                  // [N]
+    float* out_f32;                     // [M,N]  (EPI_F32: written; EPI_RESID: out += acc + bias)
+    __nv_bfloat16 *out_hi, *out_lo;     // [M,N]  (EPI_GELU_SPLIT)
+    long long M;
+    int N, K;
+    int epilogue;
+};
+
+int launch_split_weights(const float* w, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
+int launch_time_mlp(const float* sinus, const float* w1, const float* b1, const float* w2, const float* b2,
+                    float* temb, int C, cudaStream_t st);
+int launch_embed(const EmbedParams& p, cudaStream_t st);
+int launch_ln_chain(const LnParams& p, cudaStream_t st);
+int launch_head(const HeadParams& p, cudaStream_t st);
+int launch_ddim_step(const DdimParams& p, cudaStream_t st);
+int launch_reassemble(const float* in, float* out, const int* conn_of_joint, long long poses, int num_kps,
+                      cudaStream_t st);
+int launch_negate_rows(float* x, const int* rows, int nrows, long long poses, int num_kps, cudaStream_t st);
+int launch_project(const float* X, const float* cam, float* out, long long npts, long long pts_per_cam,
+                   cudaStream_t st);
+int launch_aggregate(const AggParams& p, cudaStream_t st);
+int launch_attention(const AttnParams& p, cudaStream_t st);
+
+// tcgen05 GEMM (bf16x3 split precision).  Tensor maps are built per call from the raw pointers.
+int gemm_init();                                            // resolves cuTensorMapEncodeTiled
+int launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t st);
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);   // debug reference (CUDA cores)
+int gemm_pick_block_n(int N);
+
+}  // namespace pafuse

@@ -1,0 +1,575 @@
+// C ABI (include/pafuse_b200.h): context, weight store, workspace and the
+// orchestration of one denoiser pass / one DDIM step out of the sm_100a kernels.
+#include "../../include/pafuse_b200.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace pafuse {
+
+static thread_local char g_err[1024] = "";
+thread_local long long g_launch_count = 0;
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct Slot {
+    size_t off = 0;      // element offset inside the part arena
+    size_t numel = 0;
+    bool gemm = false;   // needs a bf16 hi/lo copy
+    bool set = false;
+};
+
+struct Part {
+    int C = 0, J = 0;
+    std::map<std::string, Slot> slots;
+    size_t total = 0;
+    float* f32 = nullptr;
+    __nv_bfloat16* hi = nullptr;
+    __nv_bfloat16* lo = nullptr;
+    int* joints_dev = nullptr;
+    float* temb = nullptr;
+
+    const float* w(const std::string& n) const { return f32 + slots.at(n).off; }
+    const __nv_bfloat16* wh(const std::string& n) const { return hi + slots.at(n).off; }
+    const __nv_bfloat16* wl(const std::string& n) const { return lo + slots.at(n).off; }
+};
+
+struct Workspace {
+    long long rows_x_c = 0;   // capacity in (rows * C) units
+    float* x = nullptr;
+    __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr;
+    float* qkv = nullptr;
+    __nv_bfloat16 *o_hi = nullptr, *o_lo = nullptr;
+    __nv_bfloat16 *h_hi = nullptr, *h_lo = nullptr;
+};
+
+}  // namespace pafuse
+
+using namespace pafuse;
+
+struct pafuse_ctx {
+    pafuse_config cfg;
+    int device = 0;
+    int num_parts = 0;
+    Part parts[PAFUSE_MAX_PARTS];
+    int* flip_perm_dev = nullptr;
+    int* conn_dev = nullptr;         // scratch for wb_pose_from_parts tables
+    int* conn_rows_dev = nullptr;
+    Workspace ws;
+    float* pred = nullptr;           // [S,F,num_kps,3]
+    size_t pred_cap = 0;             // floats
+    bool committed = false;
+    bool debug_simt = false;
+};
+
+namespace {
+
+void add_slot(Part& p, const std::string& name, size_t numel, bool gemm = false) {
+    Slot s;
+    s.off = p.total;
+    s.numel = numel;
+    s.gemm = gemm;
+    p.slots[name] = s;
+    p.total += (numel + 63) / 64 * 64;   // 256-byte alignment (TMA needs 16 B on the bf16 copies)
+}
+
+// tensor table of one MixSTE2 denoiser (common/mixste.py:141-210)
+void build_part_table(Part& p, int C, int J, int F, int depth) {
+    p.C = C;
+    p.J = J;
+    size_t c = (size_t)C;
+    add_slot(p, "Spatial_patch_to_embedding.weight", c * 5);
+    add_slot(p, "Spatial_patch_to_embedding.bias", c);
+    add_slot(p, "Spatial_pos_embed", (size_t)J * c);
+    add_slot(p, "Temporal_pos_embed", (size_t)F * c);
+    add_slot(p, "time_mlp.1.weight", 2 * c * c);
+    add_slot(p, "time_mlp.1.bias", 2 * c);
+    add_slot(p, "time_mlp.3.weight", 2 * c * c);
+    add_slot(p, "time_mlp.3.bias", c);
+    add_slot(p, "Spatial_norm.weight", c);
+    add_slot(p, "Spatial_norm.bias", c);
+    add_slot(p, "Temporal_norm.weight", c);
+    add_slot(p, "Temporal_norm.bias", c);
+    add_slot(p, "head.0.weight", c);
+    add_slot(p, "head.0.bias", c);
+    add_slot(p, "head.1.weight", 3 * c);
+    add_slot(p, "head.1.bias", 3);
+    const char* stacks[2] = {"STEblocks", "TTEblocks"};
+    for (int st = 0; st < 2; ++st)
+        for (int i = 0; i < depth; ++i) {
+            std::string b = std::string(stacks[st]) + "." + std::to_string(i) + ".";
+            add_slot(p, b + "norm1.weight", c);
+            add_slot(p, b + "norm1.bias", c);
+            add_slot(p, b + "attn.qkv.weight", 3 * c * c, true);
+            add_slot(p, b + "attn.qkv.bias", 3 * c);
+            add_slot(p, b + "attn.proj.weight", c * c, true);
+            add_slot(p, b + "attn.proj.bias", c);
+            add_slot(p, b + "norm2.weight", c);
+            add_slot(p, b + "norm2.bias", c);
+            add_slot(p, b + "mlp.fc1.weight", 2 * c * c, true);
+            add_slot(p, b + "mlp.fc1.bias", 2 * c);
+            add_slot(p, b + "mlp.fc2.weight", 2 * c * c, true);
+            add_slot(p, b + "mlp.fc2.bias", c);
+        }
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t n) {
+    PAFUSE_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+    return 0;
+}
+
+int ensure_workspace(pafuse_ctx* ctx, long long rows_x_c) {
+    Workspace& w = ctx->ws;
+    if (rows_x_c <= w.rows_x_c) return 0;
+    cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv);
+    cudaFree(w.o_hi); cudaFree(w.o_lo); cudaFree(w.h_hi); cudaFree(w.h_lo);
+    w = Workspace();
+    size_t n = (size_t)rows_x_c;
+    if (dev_alloc(&w.x, n)) return PAFUSE_E_CUDA;
+    if (dev_alloc(&w.a_hi, n) || dev_alloc(&w.a_lo, n)) return PAFUSE_E_CUDA;
+    if (dev_alloc(&w.qkv, 3 * n)) return PAFUSE_E_CUDA;
+    if (dev_alloc(&w.o_hi, n) || dev_alloc(&w.o_lo, n)) return PAFUSE_E_CUDA;
+    if (dev_alloc(&w.h_hi, 2 * n) || dev_alloc(&w.h_lo, 2 * n)) return PAFUSE_E_CUDA;
+    w.rows_x_c = rows_x_c;
+    return 0;
+}
+
+int ensure_pred(pafuse_ctx* ctx, size_t floats) {
+    if (floats <= ctx->pred_cap) return 0;
+    cudaFree(ctx->pred);
+    ctx->pred = nullptr;
+    ctx->pred_cap = 0;
+    if (dev_alloc(&ctx->pred, floats)) return PAFUSE_E_CUDA;
+    ctx->pred_cap = floats;
+    return 0;
+}
+
+int run_gemm(pafuse_ctx* ctx, const GemmArgs& g, cudaStream_t st) {
+    return ctx->debug_simt ? launch_gemm_simt(g, st) : launch_gemm_tcgen05(g, st);
+}
+
+// One pass of the three part denoisers over S_total sequences (R originals followed,
+// when S_total == 2R, by their flip-TTA twins), chunked by cfg.max_seqs.
+int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, const float* x3d, int apply_clamp, int R,
+                  int H, int S_total, const float* sinus, float* pred, cudaStream_t st) {
+    const pafuse_config& cfg = ctx->cfg;
+    const int F = cfg.frames;
+    if (!ctx->committed) {
+        set_last_error("weights not committed (call pafuse_commit_weights)");
+        return PAFUSE_E_STATE;
+    }
+    // time embedding per part (identical for every row: the sampler uses one t per call)
+    {
+        int off = 0;
+        for (int pi = 0; pi < ctx->num_parts; ++pi) {
+            Part& p = ctx->parts[pi];
+            if (int rc = launch_time_mlp(sinus + off, p.w("time_mlp.1.weight"), p.w("time_mlp.1.bias"),
+                                         p.w("time_mlp.3.weight"), p.w("time_mlp.3.bias"), p.temb, p.C, st))
+                return rc;
+            off += p.C;
+        }
+    }
+    int max_seqs = cfg.max_seqs > 0 ? cfg.max_seqs : 256;
+    int chunk = S_total < max_seqs ? S_total : max_seqs;
+    long long need = 0;
+    for (int pi = 0; pi < ctx->num_parts; ++pi) {
+        long long v = (long long)chunk * F * ctx->parts[pi].J * ctx->parts[pi].C;
+        if (v > need) need = v;
+    }
+    if (int rc = ensure_workspace(ctx, need)) return rc;
+    Workspace& w = ctx->ws;
+
+    for (int s0 = 0; s0 < S_total; s0 += chunk) {
+        const int Sc = (S_total - s0) < chunk ? (S_total - s0) : chunk;
+        for (int pi = 0; pi < ctx->num_parts; ++pi) {
+            Part& p = ctx->parts[pi];
+            const int C = p.C, J = p.J;
+            const long long M = (long long)Sc * F * J;
+
+            EmbedParams e;
+            e.M = M; e.C = C; e.J = J; e.F = F; e.H = H; e.R = R; e.s0 = s0; e.num_kps = cfg.num_kps;
+            e.apply_clamp = apply_clamp;
+            e.clamp = (float)(1.1 * (double)cfg.scale);
+            e.scale = cfg.scale;
+            e.x2d = x2d; e.x2d_flip = x2d_flip; e.x3d = x3d;
+            e.part_joints = p.joints_dev; e.flip_perm = ctx->flip_perm_dev;
+            e.we = p.w("Spatial_patch_to_embedding.weight"); e.be = p.w("Spatial_patch_to_embedding.bias");
+            e.spos = p.w("Spatial_pos_embed"); e.temb = p.temb; e.x = w.x;
+            if (int rc = launch_embed(e, st)) return rc;
+
+            for (int blk = 0; blk < 2 * cfg.depth; ++blk) {
+                const bool temporal = blk & 1;
+                const std::string b = std::string(temporal ? "TTEblocks." : "STEblocks.") + std::to_string(blk / 2) + ".";
+                // shared norm of the previous block (+ Temporal_pos_embed before TTE 0), then norm1 -> hi/lo
+                LnParams l;
+                l.M = M; l.C = C; l.J = J; l.F = F; l.x = w.x;
+                l.g0 = l.b0 = nullptr; l.add_f = nullptr; l.eps0 = 1e-6f;
+                if (blk > 0) {
+                    const char* sn = temporal ? "Spatial_norm" : "Temporal_norm";   // norm that closed the previous block
+                    l.g0 = p.w(std::string(sn) + ".weight");
+                    l.b0 = p.w(std::string(sn) + ".bias");
+                    if (blk == 1) l.add_f = p.w("Temporal_pos_embed");
+                }
+                l.g1 = p.w(b + "norm1.weight"); l.b1 = p.w(b + "norm1.bias"); l.eps1 = 1e-6f;
+                l.out_hi = w.a_hi; l.out_lo = w.a_lo;
+                if (int rc = launch_ln_chain(l, st)) return rc;
+
+                GemmArgs g;
+                g.a_hi = w.a_hi; g.a_lo = w.a_lo;
+                g.w_hi = p.wh(b + "attn.qkv.weight"); g.w_lo = p.wl(b + "attn.qkv.weight");
+                g.bias = p.w(b + "attn.qkv.bias");
+                g.out_f32 = w.qkv; g.out_hi = g.out_lo = nullptr;
+                g.M = M; g.N = 3 * C; g.K = C; g.epilogue = EPI_F32;
+                if (int rc = run_gemm(ctx, g, st)) return rc;
+
+                AttnParams a;
+                a.qkv = w.qkv; a.out_hi = w.o_hi; a.out_lo = w.o_lo;
+                a.S = Sc; a.F = F; a.J = J; a.C = C; a.temporal = temporal ? 1 : 0; a.scale = 0.f;
+                if (int rc = launch_attention(a, st)) return rc;
+
+                g.a_hi = w.o_hi; g.a_lo = w.o_lo;
+                g.w_hi = p.wh(b + "attn.proj.weight"); g.w_lo = p.wl(b + "attn.proj.weight");
+                g.bias = p.w(b + "attn.proj.bias");
+                g.out_f32 = w.x; g.N = C; g.K = C; g.epilogue = EPI_RESID;
+                if (int rc = run_gemm(ctx, g, st)) return rc;
+
+                l.g0 = l.b0 = nullptr; l.add_f = nullptr;
+                l.g1 = p.w(b + "norm2.weight"); l.b1 = p.w(b + "norm2.bias");
+                if (int rc = launch_ln_chain(l, st)) return rc;
+
+                g.a_hi = w.a_hi; g.a_lo = w.a_lo;
+                g.w_hi = p.wh(b + "mlp.fc1.weight"); g.w_lo = p.wl(b + "mlp.fc1.weight");
+                g.bias = p.w(b + "mlp.fc1.bias");
+                g.out_f32 = nullptr; g.out_hi = w.h_hi; g.out_lo = w.h_lo;
+                g.N = 2 * C; g.K = C; g.epilogue = EPI_GELU_SPLIT;
+                if (int rc = run_gemm(ctx, g, st)) return rc;
+
+                g.a_hi = w.h_hi; g.a_lo = w.h_lo;
+                g.w_hi = p.wh(b + "mlp.fc2.weight"); g.w_lo = p.wl(b + "mlp.fc2.weight");
+                g.bias = p.w(b + "mlp.fc2.bias");
+                g.out_f32 = w.x; g.out_hi = g.out_lo = nullptr;
+                g.N = C; g.K = 2 * C; g.epilogue = EPI_RESID;
+                if (int rc = run_gemm(ctx, g, st)) return rc;
+            }
+
+            HeadParams h;
+            h.M = M; h.C = C; h.J = J; h.F = F; h.s0 = s0; h.num_kps = cfg.num_kps; h.x = w.x;
+            h.g0 = p.w("Temporal_norm.weight"); h.b0 = p.w("Temporal_norm.bias"); h.eps0 = 1e-6f;
+            h.g1 = p.w("head.0.weight"); h.b1 = p.w("head.0.bias"); h.eps1 = 1e-5f;
+            h.wh = p.w("head.1.weight"); h.bh = p.w("head.1.bias");
+            h.part_joints = p.joints_dev; h.pred = pred;
+            if (int rc = launch_head(h, st)) return rc;
+        }
+    }
+    return 0;
+}
+
+bool check_ctx(pafuse_ctx* ctx) {
+    if (!ctx) {
+        set_last_error("null context");
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pafuse_last_error(void) { return g_err; }
+const char* pafuse_version(void) { return "pafuse_b200 0.1 (sm_100a, tcgen05 bf16x3)"; }
+int64_t pafuse_launch_count(void) { return (int64_t)g_launch_count; }
+
+int pafuse_create(const pafuse_config* cfg, pafuse_ctx** out) {
+    if (!cfg || !out) {
+        set_last_error("pafuse_create: null argument");
+        return PAFUSE_E_ARG;
+    }
+    if (cfg->num_parts < 1 || cfg->num_parts > PAFUSE_MAX_PARTS || cfg->heads != 8 || cfg->frames < 1 ||
+        cfg->depth < 1 || cfg->num_kps < 1 || !cfg->flip_perm) {
+        set_last_error("pafuse_create: bad config (parts=%d heads=%d frames=%d depth=%d)", cfg->num_parts, cfg->heads,
+                       cfg->frames, cfg->depth);
+        return PAFUSE_E_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_last_error("pafuse_create: no CUDA device (this library has no CPU fallback)");
+        return PAFUSE_E_CUDA;
+    }
+    pafuse_ctx* ctx = new pafuse_ctx();
+    ctx->cfg = *cfg;
+    ctx->num_parts = cfg->num_parts;
+    PAFUSE_CUDA_OK(cudaGetDevice(&ctx->device));
+    cudaDeviceProp prop;
+    PAFUSE_CUDA_OK(cudaGetDeviceProperties(&prop, ctx->device));
+    if (prop.major != 10) {
+        set_last_error("pafuse_create: device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor);
+        delete ctx;
+        return PAFUSE_E_CUDA;
+    }
+    for (int pi = 0; pi < cfg->num_parts; ++pi) {
+        Part& p = ctx->parts[pi];
+        int C = cfg->part_channels[pi], J = cfg->part_num_joints[pi];
+        if (C % 32 != 0 || C > 384 || J < 1 || !cfg->part_joints[pi]) {
+            set_last_error("pafuse_create: part %d has unsupported C=%d J=%d", pi, C, J);
+            delete ctx;
+            return PAFUSE_E_ARG;
+        }
+        build_part_table(p, C, J, cfg->frames, cfg->depth);
+        if (dev_alloc(&p.f32, p.total) || dev_alloc(&p.hi, p.total) || dev_alloc(&p.lo, p.total) ||
+            dev_alloc(&p.joints_dev, (size_t)J) || dev_alloc(&p.temb, (size_t)C))
+            return PAFUSE_E_CUDA;
+        PAFUSE_CUDA_OK(cudaMemset(p.f32, 0, p.total * sizeof(float)));
+        PAFUSE_CUDA_OK(cudaMemcpy(p.joints_dev, cfg->part_joints[pi], J * sizeof(int), cudaMemcpyHostToDevice));
+        ctx->cfg.part_joints[pi] = nullptr;   // host pointer not retained
+    }
+    if (dev_alloc(&ctx->flip_perm_dev, (size_t)cfg->num_kps) || dev_alloc(&ctx->conn_dev, (size_t)cfg->num_kps) ||
+        dev_alloc(&ctx->conn_rows_dev, (size_t)cfg->num_kps))
+        return PAFUSE_E_CUDA;
+    PAFUSE_CUDA_OK(cudaMemcpy(ctx->flip_perm_dev, cfg->flip_perm, cfg->num_kps * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->cfg.flip_perm = nullptr;
+    if (int rc = gemm_init()) return rc;
+    *out = ctx;
+    return 0;
+}
+
+void pafuse_destroy(pafuse_ctx* ctx) {
+    if (!ctx) return;
+    for (int pi = 0; pi < ctx->num_parts; ++pi) {
+        Part& p = ctx->parts[pi];
+        cudaFree(p.f32); cudaFree(p.hi); cudaFree(p.lo); cudaFree(p.joints_dev); cudaFree(p.temb);
+    }
+    Workspace& w = ctx->ws;
+    cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv);
+    cudaFree(w.o_hi); cudaFree(w.o_lo); cudaFree(w.h_hi); cudaFree(w.h_lo);
+    cudaFree(ctx->flip_perm_dev); cudaFree(ctx->conn_dev); cudaFree(ctx->conn_rows_dev); cudaFree(ctx->pred);
+    delete ctx;
+}
+
+int pafuse_set_weight(pafuse_ctx* ctx, int32_t part, const char* name, const float* data, int64_t numel,
+                      int32_t on_device) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (part < 0 || part >= ctx->num_parts || !name || !data) {
+        set_last_error("pafuse_set_weight: bad argument (part=%d)", part);
+        return PAFUSE_E_ARG;
+    }
+    Part& p = ctx->parts[part];
+    auto it = p.slots.find(name);
+    if (it == p.slots.end()) {
+        set_last_error("pafuse_set_weight: unknown tensor '%s'", name);
+        return PAFUSE_E_ARG;
+    }
+    if ((size_t)numel != it->second.numel) {
+        set_last_error("pafuse_set_weight: '%s' expects %zu elements, got %lld", name, it->second.numel, (long long)numel);
+        return PAFUSE_E_ARG;
+    }
+    PAFUSE_CUDA_OK(cudaMemcpy(p.f32 + it->second.off, data, (size_t)numel * sizeof(float),
+                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    it->second.set = true;
+    ctx->committed = false;
+    return 0;
+}
+
+int pafuse_commit_weights(pafuse_ctx* ctx, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int pi = 0; pi < ctx->num_parts; ++pi) {
+        Part& p = ctx->parts[pi];
+        for (auto& kv : p.slots) {
+            if (!kv.second.set) {
+                set_last_error("pafuse_commit_weights: part %d tensor '%s' was never set", pi, kv.first.c_str());
+                return PAFUSE_E_STATE;
+            }
+            if (kv.second.gemm)
+                if (int rc = launch_split_weights(p.f32 + kv.second.off, p.hi + kv.second.off, p.lo + kv.second.off,
+                                                  kv.second.numel, st))
+                    return rc;
+        }
+    }
+    ctx->committed = true;
+    return 0;
+}
+
+int pafuse_pred_parts(pafuse_ctx* ctx, const float* x2d, const float* x3d, const float* sinus, float* out, int32_t B,
+                      int32_t H, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!x2d || !x3d || !sinus || !out || B < 0 || H < 1) {
+        set_last_error("pafuse_pred_parts: bad argument");
+        return PAFUSE_E_ARG;
+    }
+    if (B == 0) return 0;
+    return run_denoisers(ctx, x2d, nullptr, x3d, 0, B * H, H, B * H, sinus, out, (cudaStream_t)stream);
+}
+
+int pafuse_ddim_step(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, const float* sinus, float* img,
+                     const float* noise, float* x0_out, int64_t x0_batch_stride, int32_t B, int32_t H, int32_t flip,
+                     int32_t last, double sqrt_recip, double sqrt_recipm1, double c64, float sqrt_an, float c,
+                     float sigma, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!x2d || !sinus || !img || !x0_out || B < 0 || H < 1 || (flip && !x2d_flip) || (!last && !noise)) {
+        set_last_error("pafuse_ddim_step: bad argument");
+        return PAFUSE_E_ARG;
+    }
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const pafuse_config& cfg = ctx->cfg;
+    const int R = B * H;
+    const int S_total = flip ? 2 * R : R;
+    if (int rc = ensure_pred(ctx, (size_t)S_total * cfg.frames * cfg.num_kps * 3)) return rc;
+    if (int rc = run_denoisers(ctx, x2d, x2d_flip, img, 1, R, H, S_total, sinus, ctx->pred, st)) return rc;
+    DdimParams d;
+    d.R = R; d.F = cfg.frames; d.H = H; d.num_kps = cfg.num_kps; d.flip = flip ? 1 : 0; d.last = last ? 1 : 0;
+    d.pred = ctx->pred; d.flip_perm = ctx->flip_perm_dev; d.img = img; d.noise = noise;
+    d.x0_out = x0_out; d.x0_batch_stride = x0_batch_stride;
+    d.scale = cfg.scale; d.clamp = (float)(1.1 * (double)cfg.scale);
+    d.sqrt_recip = sqrt_recip; d.sqrt_recipm1 = sqrt_recipm1; d.c64 = c64;
+    d.sqrt_an = sqrt_an; d.c = c; d.sigma = sigma;
+    return launch_ddim_step(d, st);
+}
+
+int pafuse_wb_pose_from_parts(pafuse_ctx* ctx, float* pose, float* out, const int32_t* conn_of_joint, int64_t poses,
+                              int32_t mutate_input, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!pose || !out || !conn_of_joint || pose == out || poses < 0) {
+        set_last_error("pafuse_wb_pose_from_parts: bad argument (in-place use is not supported)");
+        return PAFUSE_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nk = ctx->cfg.num_kps;
+    std::vector<int> rows;
+    for (int g = 0; g < nk; ++g) {
+        int r = conn_of_joint[g];
+        if (r >= nk) {
+            set_last_error("pafuse_wb_pose_from_parts: connection index %d out of range", r);
+            return PAFUSE_E_ARG;
+        }
+        bool seen = false;
+        for (int v : rows) seen |= (v == r);
+        if (r >= 0 && !seen) rows.push_back(r);
+    }
+    PAFUSE_CUDA_OK(cudaMemcpyAsync(ctx->conn_dev, conn_of_joint, nk * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (int rc = launch_reassemble(pose, out, ctx->conn_dev, poses, nk, st)) return rc;
+    if (mutate_input && !rows.empty()) {
+        PAFUSE_CUDA_OK(cudaMemcpyAsync(ctx->conn_rows_dev, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (int rc = launch_negate_rows(pose, ctx->conn_rows_dev, (int)rows.size(), poses, nk, st)) return rc;
+    }
+    // the two small table uploads read pageable host memory: make them complete before returning
+    PAFUSE_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int pafuse_project_to_2d(pafuse_ctx* ctx, const float* X, const float* cam, float* out, int64_t n_cams,
+                         int64_t pts_per_cam, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!X || !cam || !out || n_cams < 0 || pts_per_cam < 1) {
+        set_last_error("pafuse_project_to_2d: bad argument");
+        return PAFUSE_E_ARG;
+    }
+    return launch_project(X, cam, out, n_cams * pts_per_cam, pts_per_cam, (cudaStream_t)stream);
+}
+
+int pafuse_aggregate(pafuse_ctx* ctx, const float* pred, const float* traj, const float* cam, int32_t cam_per_clip,
+                     const float* x2d, float* jagg, float* pagg, int32_t* select, float* reproj, int32_t B, int32_t K,
+                     int32_t H, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!pred || !cam || !x2d || !jagg || !pagg || B < 0 || K < 1 || H < 1) {
+        set_last_error("pafuse_aggregate: bad argument");
+        return PAFUSE_E_ARG;
+    }
+    AggParams a;
+    a.B = B; a.K = K; a.H = H; a.F = ctx->cfg.frames; a.J = ctx->cfg.num_kps; a.cam_per_clip = cam_per_clip;
+    a.pred = pred; a.traj = traj; a.cam = cam; a.x2d = x2d; a.jagg = jagg; a.pagg = pagg; a.select = select;
+    a.reproj = reproj;
+    return launch_aggregate(a, (cudaStream_t)stream);
+}
+
+int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    ctx->debug_simt = enable != 0;
+    return 0;
+}
+
+// ---- unit-level entry points -------------------------------------------------------------
+
+__global__ void split_rows_kernel(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) split_bf16(x[i], hi[i], lo[i]);
+}
+__global__ void join_rows_kernel(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* y, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+
+int pafuse_linear(pafuse_ctx* ctx, const float* x, const float* w, const float* b, float* y, int64_t M, int32_t N,
+                  int32_t K, int32_t epilogue, int32_t use_simt, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!x || !w || !b || !y || M < 1 || N < 1 || K < 1 || epilogue < 0 || epilogue > 2) {
+        set_last_error("pafuse_linear: bad argument");
+        return PAFUSE_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16 *xh = nullptr, *xl = nullptr, *wh = nullptr, *wl = nullptr, *yh = nullptr, *yl = nullptr;
+    size_t nx = (size_t)M * K, nw = (size_t)N * K, ny = (size_t)M * N;
+    int rc = 0;
+    if (dev_alloc(&xh, nx) || dev_alloc(&xl, nx) || dev_alloc(&wh, nw) || dev_alloc(&wl, nw)) rc = PAFUSE_E_CUDA;
+    if (!rc && epilogue == EPI_GELU_SPLIT && (dev_alloc(&yh, ny) || dev_alloc(&yl, ny))) rc = PAFUSE_E_CUDA;
+    if (!rc) {
+        split_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(x, xh, xl, nx);
+        split_rows_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, wh, wl, nw);
+        GemmArgs g;
+        g.a_hi = xh; g.a_lo = xl; g.w_hi = wh; g.w_lo = wl; g.bias = b; g.out_f32 = y; g.out_hi = yh; g.out_lo = yl;
+        g.M = M; g.N = N; g.K = K; g.epilogue = epilogue;
+        rc = use_simt ? launch_gemm_simt(g, st) : launch_gemm_tcgen05(g, st);
+        if (!rc && epilogue == EPI_GELU_SPLIT) join_rows_kernel<<<(unsigned)((ny + 255) / 256), 256, 0, st>>>(yh, yl, y, ny);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(xh); cudaFree(xl); cudaFree(wh); cudaFree(wl); cudaFree(yh); cudaFree(yl);
+    if (!rc && e != cudaSuccess) {
+        set_last_error("pafuse_linear: %s", cudaGetErrorString(e));
+        rc = PAFUSE_E_CUDA;
+    }
+    return rc;
+}
+
+int pafuse_attention(pafuse_ctx* ctx, const float* qkv, float* out, int32_t S, int32_t J, int32_t C, int32_t temporal,
+                     void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!qkv || !out || S < 1) {
+        set_last_error("pafuse_attention: bad argument");
+        return PAFUSE_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t n = (size_t)S * ctx->cfg.frames * J * C;
+    __nv_bfloat16 *oh = nullptr, *ol = nullptr;
+    int rc = 0;
+    if (dev_alloc(&oh, n) || dev_alloc(&ol, n)) rc = PAFUSE_E_CUDA;
+    if (!rc) {
+        AttnParams a;
+        a.qkv = qkv; a.out_hi = oh; a.out_lo = ol; a.S = S; a.F = ctx->cfg.frames; a.J = J; a.C = C;
+        a.temporal = temporal; a.scale = 0.f;
+        rc = launch_attention(a, st);
+        if (!rc) join_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(oh, ol, out, n);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(oh); cudaFree(ol);
+    if (!rc && e != cudaSuccess) {
+        set_last_error("pafuse_attention: %s", cudaGetErrorString(e));
+        rc = PAFUSE_E_CUDA;
+    }
+    return rc;
+}
+
+}  // extern "C"
