@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Headline benchmark: whole-body 3D frames/s of the PAFUSE lifting path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full lift of one batch of synthetic clips: D3DP.forward (H hypotheses x K DDIM
+steps, flip-TTA) -> wb_pose_from_parts -> J-Agg / P-Agg.  Workload = BASELINE.json configs[1]
+(H3WB config.yaml eval shape, num_proposals=5, sampling_timesteps=5) with 64 clips (1728 frames)
+per GPU; with N GPUs every rank lifts its own 64 clips (clip sharding, weak scaling) and the
+aggregated poses are all-gathered over NCCL inside the step.  Random-init weights, synthetic 2D.
+
+Prints ONE JSON line on rank 0 (see README / DESIGN.md "Measurement" for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_FORWARD_R1 = 69_384_706_048          # one pred_parts call at R=1 (matmuls only)
+FRAMES = 27
+
+
+def flops_per_frame(H, K, flip=True):
+    return FLOP_PER_FORWARD_R1 * (2 if flip else 1) * H * K / FRAMES
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on the host cores (test infrastructure used
+# here only as the *baseline being reported*, never on the product path).
+# ---------------------------------------------------------------------------------------------
+def cpu_lift_sample(H, K, clips=1, threads=None, depth=8):
+    """Time one lift of `clips` clips (same H, K, flip-TTA, depth) with the oracle on the CPU."""
+    import torch
+
+    from oracle import pafuse_oracle as orc
+    from pafuse_b200 import synthetic
+    from pafuse_b200.h3wb import H3WBSkeleton, merged_part_indices
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sk = H3WBSkeleton()
+    sd = synthetic.synthetic_state_dict(seed=1, depth=depth)
+    x2d, x2df = synthetic.synthetic_inputs(clips, seed=1)
+    noises = synthetic.synthetic_noise(clips, H, K, seed=1)
+    traj, cam = synthetic.synthetic_trajectory(clips, seed=1), synthetic.h36m_cam0_intrinsics()
+    parts = merged_part_indices(sk.parts_joint_indices)
+
+    def run():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            out = orc.ddim_sample_flip(sd, parts, x2d, x2df, noises, sk.joints_left, sk.joints_right, H, K, depth=depth)
+            wb, _ = orc.wb_pose_from_parts(out, sk.parts_joint_indices, sk.parts_connection_indices)
+            orc.aggregate(wb, traj, cam, x2d)
+        return time.perf_counter() - t0
+    return run, threads
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port; the reference itself is
+    Python and does not exist on the GPU box) with all host threads, one bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    H, K = args.proposals, args.timesteps
+    clips = args.cpu_clips
+    run, threads = cpu_lift_sample(H, K, clips=clips)
+    for _ in range(args.warmup):
+        run()
+    times = [run() for _ in range(args.steps)]
+    sec = sum(times) / len(times)
+    fps = clips * FRAMES / sec
+    sample = f"{clips} clip(s) x {FRAMES} frames of the {args.clips}-clip batch per step, H={H} K={K} flip-TTA depth 8"
+    line = {
+        "impl": "reference", "metric": "whole-body 3D frames/sec", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE configs[1]: H3WB config.yaml eval shape, {args.clips} clips x 27 frames x 134 kps per GPU, "
+                        f"num_proposals={args.proposals}, sampling_timesteps={args.timesteps}, flip-TTA, depth 8, "
+                        "lift = D3DP.forward + wb_pose_from_parts + J-Agg/P-Agg",
+            "clips_per_gpu": args.clips, "num_proposals": args.proposals, "sampling_timesteps": args.timesteps,
+            "parallelism": f"clip-sharded x{args.gpus}", "l2": "L2 flushed (512 MiB write) before every timed step"}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import pafuse_b200
+    from pafuse_b200 import distributed as pd
+    from pafuse_b200 import synthetic, utils
+    from pafuse_b200.h3wb import H3WBSkeleton
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the pafuse_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, K, Bl = args.proposals, args.timesteps, args.clips
+    B = Bl * world
+    sk = H3WBSkeleton()
+    model = pafuse_b200.D3DP(synthetic.default_args(depth=8), sk.joints_left, sk.joints_right, sk, is_train=False,
+                             num_proposals=H, sampling_timesteps=K)
+    model.load_state_dict(synthetic.synthetic_state_dict(seed=1, depth=8), strict=False)
+    model = model.to(dev).eval()
+    engine = pd.CudaEngine(model, sk)
+    x2d_h, x2df_h = synthetic.synthetic_inputs(B, seed=1)
+    traj_h, cam_h = synthetic.synthetic_trajectory(B, seed=1), synthetic.h36m_cam0_intrinsics()
+    x2d_h, x2df_h, traj_h = x2d_h.pin_memory(), x2df_h.pin_memory(), traj_h.pin_memory()
+    x2d, x2df, traj, cam = x2d_h.to(dev), x2df_h.to(dev), traj_h.to(dev), cam_h.to(dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    out_h = [torch.empty((B, K, FRAMES, 134, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+    ctx, post = model.native_context(dev), utils._post_context(dev)
+
+    def step_resident(seed):
+        return pd.lift_sharded(engine, x2d, x2df, traj, cam, H, mode="clips", seed=seed, rank=rank, world=world)
+
+    def step_e2e(seed):
+        a, b, t = x2d_h.to(dev, non_blocking=True), x2df_h.to(dev, non_blocking=True), traj_h.to(dev, non_blocking=True)
+        res = pd.lift_sharded(engine, a, b, t, cam, H, mode="clips", seed=seed, rank=rank, world=world)
+        out_h[0].copy_(res.jagg, non_blocking=True)
+        out_h[1].copy_(res.pagg, non_blocking=True)
+        return res
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(1000 + i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total = 0.0
+        for i in range(steps):
+            flush.zero_()                                              # evict L2 between timed iterations (not timed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(i)
+            b.record()
+            b.synchronize()
+            total += a.elapsed_time(b)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([total], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)                   # max over ranks
+            total = float(t.item())
+        return total / steps
+
+    sampler = ClockSampler(local)
+    launches0 = ctx.launch_count()
+    ctx.profile_enable(True)
+    post.profile_enable(True)
+    for i in range(args.warmup):
+        step_resident(1000 + i)
+    torch.cuda.synchronize()
+    ctx.profile_enable(True)                                           # drop the warm-up records
+    post.profile_enable(True)
+    launches0 = ctx.launch_count()
+    sampler.start()
+    ms = timed(step_resident, args.steps, 0)
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    prof = ctx.profile_read()
+    prof_post = post.profile_read()
+    ctx.profile_enable(False)
+    post.profile_enable(False)
+    ms_e2e = timed(step_e2e, args.steps, 1)
+
+    frames = B * FRAMES
+    fps, fps_e2e = frames / (ms * 1e-3), frames / (ms_e2e * 1e-3)
+    peaks = load_peaks()
+    g_ms, g_flops, g_n = prof["gemm"]
+    gemm_tflops = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    tensor_peak = peaks["bf16_tflops_sustained"]                       # the GEMMs are timed inside a long step
+    step_total_ms = sum(v[0] for v in prof.values()) + sum(v[0] for v in prof_post.values())
+    breakdown = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
+                     ("tflops" if k in ("gemm", "attention") else "gbs"):
+                         (v[1] / (v[0] * 1e-3) / (1e12 if k in ("gemm", "attention") else 1e9)) if v[0] > 0 else 0.0}
+                 for k, v in {**prof, "post": prof_post["post"]}.items()}
+    line = {
+        "metric": "whole-body 3D frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (fp32 operands split into bf16 hi/lo, fp32 accumulate)", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int((x2d_h.numel() + x2df_h.numel() + traj_h.numel()) * 4),
+                "d2h_bytes_per_step": int(2 * out_h[0].numel() * 4)},
+        "gpu_launches": int(launches * world),
+        "clocks": clocks,
+        "roofline": {
+            "kernel": "gemm_bf16x3_kernel (qkv/proj/fc1/fc2 of the STE/TTE blocks)",
+            "bound": "tensor", "achieved": gemm_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
+            "frac": gemm_tflops / tensor_peak, "traffic": None,
+            "peak_source": f"{peaks['source']} bf16_tflops_sustained",
+            "note": "achieved = algorithmic 2*M*N*K of the fp32 layer (the 3 bf16 tensor-core passes are not "
+                    "counted) / summed CUDA-event time of the GEMM launches in the timed region, rank 0",
+            "share_of_step": g_ms / step_total_ms if step_total_ms else None,
+            "launches": g_n,
+            "path_tflops": fps / world * flops_per_frame(H, K) / 1e12,
+            "path_frac": fps / world * flops_per_frame(H, K) / 1e12 / tensor_peak,
+        },
+        "kernel_breakdown": breakdown,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        run, threads = cpu_lift_sample(H, K, clips=args.cpu_clips)
+        sec = run()
+        line["cpu_baseline"] = {"value": args.cpu_clips * FRAMES / sec, "unit": "frames/s", "cores": threads,
+                                "kind": "port", "sample": f"{args.cpu_clips} clip(s) of the {Bl}-clip batch, H={H} K={K}, "
+                                                          f"one pass ({sec:.1f} s)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=64, help="clips per GPU (weak scaling)")
+    ap.add_argument("--proposals", type=int, default=5)
+    ap.add_argument("--timesteps", type=int, default=5)
+    ap.add_argument("--cpu-clips", type=int, default=1, help="clips in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -113,6 +113,16 @@ int pafuse_aggregate(pafuse_ctx* ctx, const float* pred, const float* traj, cons
                      const float* x2d, float* jagg, float* pagg, int32_t* select, float* reproj, int32_t B, int32_t K,
                      int32_t H, void* stream);
 
+/* Per-launch device timing for the roofline leg of bench.py: while enabled, every kernel this
+ * context launches is bracketed by CUDA events on the launching stream.  pafuse_profile_read
+ * synchronises and returns, per category (0 tensor-core GEMM, 1 attention, 2 LayerNorm chain,
+ * 3 embed/time-MLP/head, 4 DDIM update, 5 re-assembly + aggregation), the summed device time in
+ * ms, the algorithmic work (FLOPs for 0-1, bytes for 2-5) and the launch count.  Enabling again
+ * (or disabling) clears the records. */
+#define PAFUSE_PROFILE_CATEGORIES 6
+int pafuse_profile_enable(pafuse_ctx* ctx, int32_t enable);
+int pafuse_profile_read(pafuse_ctx* ctx, double* ms, double* work, int64_t* launches, int32_t ncat);
+
 /* ---- unit-level entry points (tests and profiling; same kernels the path uses) ---- */
 
 /* y = x W^T + b through the tcgen05 bf16x3 GEMM (use_simt != 0: CUDA-core debug reference).

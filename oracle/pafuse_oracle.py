@@ -254,6 +254,17 @@ def wb_pose_from_parts(pose: torch.Tensor, parts_joint_indices: dict, connection
     return out, x
 
 
+def center_pose_parts(pose: torch.Tensor, parts_joint_indices: dict, root_indices: dict) -> torch.Tensor:
+    """Part-centred pose (applied to the GROUND TRUTH by the callers, main_h3wb.py:304):
+    out[part joints] = x[part joints] - x[root(part)]; common/utils.py:95-110 with
+    center_pose_at_root (:79-92, revert=False: no aliasing side effect)."""
+    out = torch.zeros_like(pose)
+    for part, idx in parts_joint_indices.items():
+        r = root_indices[part]
+        out[..., idx, :] = (pose - pose[..., r:r + 1, :])[..., idx, :]
+    return out
+
+
 def project_to_2d(X: torch.Tensor, cam: torch.Tensor) -> torch.Tensor:
     """H36M projection with distortion, common/camera.py:30-60.  X (N,*,3), cam (N,9)."""
     while cam.dim() < X.dim():

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "pafuse_project_to_2d": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "pafuse_aggregate": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "pafuse_profile_enable": (c_int32, [c_void_p, c_int32]),
+    "pafuse_profile_read": (c_int32, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64), c_int32]),
     "pafuse_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                 c_int32, c_void_p]),
     "pafuse_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
@@ -238,6 +240,19 @@ class NativeContext:
 
     def set_debug_simt_gemm(self, enable: bool):
         check(self.lib.pafuse_set_debug_simt_gemm(self.handle, 1 if enable else 0), "pafuse_set_debug_simt_gemm")
+
+    PROFILE_CATEGORIES = ("gemm", "attention", "layernorm", "embed_head", "ddim", "post")
+
+    def profile_enable(self, enable: bool = True):
+        check(self.lib.pafuse_profile_enable(self.handle, 1 if enable else 0), "pafuse_profile_enable")
+
+    def profile_read(self):
+        """{category: (device ms, algorithmic work, launches)} since profile_enable(True)."""
+        n = len(self.PROFILE_CATEGORIES)
+        ms, work, cnt = (c_double * n)(), (c_double * n)(), (c_int64 * n)()
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_profile_read(self.handle, ms, work, cnt, n), "pafuse_profile_read")
+        return {name: (ms[i], work[i], int(cnt[i])) for i, name in enumerate(self.PROFILE_CATEGORIES)}
 
     def launch_count(self) -> int:
         return int(self.lib.pafuse_launch_count())

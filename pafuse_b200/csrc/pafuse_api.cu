@@ -55,6 +55,32 @@ struct Workspace {
     __nv_bfloat16 *h_hi = nullptr, *h_lo = nullptr;
 };
 
+// Optional per-launch device timing (bench.py's roofline leg): CUDA events on the launching
+// stream around every kernel, summed per category when read.
+enum ProfCat { CAT_GEMM = 0, CAT_ATTN, CAT_LN, CAT_EMBED_HEAD, CAT_DDIM, CAT_POST, CAT_COUNT };
+
+struct ProfRec {
+    int cat;
+    double work;          // algorithmic FLOPs (GEMM, attention) or bytes (the rest) of this launch
+    cudaEvent_t a, b;
+};
+
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
 }  // namespace pafuse
 
 using namespace pafuse;
@@ -72,9 +98,31 @@ struct pafuse_ctx {
     size_t pred_cap = 0;             // floats
     bool committed = false;
     bool debug_simt = false;
+    Profiler prof;
 };
 
 namespace {
+
+struct ProfScope {
+    pafuse_ctx* ctx;
+    cudaStream_t st;
+    size_t idx = 0;
+    bool active;
+    ProfScope(pafuse_ctx* c, int cat, double work, cudaStream_t s) : ctx(c), st(s), active(c->prof.on) {
+        if (!active) return;
+        ProfRec r;
+        r.cat = cat;
+        r.work = work;
+        r.a = c->prof.get();
+        r.b = c->prof.get();
+        cudaEventRecord(r.a, st);
+        idx = c->prof.recs.size();
+        c->prof.recs.push_back(r);
+    }
+    ~ProfScope() {
+        if (active) cudaEventRecord(ctx->prof.recs[idx].b, st);
+    }
+};
 
 void add_slot(Part& p, const std::string& name, size_t numel, bool gemm = false) {
     Slot s;
@@ -158,6 +206,7 @@ int ensure_pred(pafuse_ctx* ctx, size_t floats) {
 }
 
 int run_gemm(pafuse_ctx* ctx, const GemmArgs& g, cudaStream_t st) {
+    ProfScope ps(ctx, CAT_GEMM, 2.0 * (double)g.M * g.N * g.K, st);
     return ctx->debug_simt ? launch_gemm_simt(g, st) : launch_gemm_tcgen05(g, st);
 }
 
@@ -176,6 +225,7 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
         int off = 0;
         for (int pi = 0; pi < ctx->num_parts; ++pi) {
             Part& p = ctx->parts[pi];
+            ProfScope ps(ctx, CAT_EMBED_HEAD, 4.0 * 4.0 * p.C * p.C, st);
             if (int rc = launch_time_mlp(sinus + off, p.w("time_mlp.1.weight"), p.w("time_mlp.1.bias"),
                                          p.w("time_mlp.3.weight"), p.w("time_mlp.3.bias"), p.temb, p.C, st))
                 return rc;
@@ -208,7 +258,10 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
             e.part_joints = p.joints_dev; e.flip_perm = ctx->flip_perm_dev;
             e.we = p.w("Spatial_patch_to_embedding.weight"); e.be = p.w("Spatial_patch_to_embedding.bias");
             e.spos = p.w("Spatial_pos_embed"); e.temb = p.temb; e.x = w.x;
-            if (int rc = launch_embed(e, st)) return rc;
+            {
+                ProfScope ps(ctx, CAT_EMBED_HEAD, 4.0 * (double)M * C, st);
+                if (int rc = launch_embed(e, st)) return rc;
+            }
 
             for (int blk = 0; blk < 2 * cfg.depth; ++blk) {
                 const bool temporal = blk & 1;
@@ -225,7 +278,10 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
                 }
                 l.g1 = p.w(b + "norm1.weight"); l.b1 = p.w(b + "norm1.bias"); l.eps1 = 1e-6f;
                 l.out_hi = w.a_hi; l.out_lo = w.a_lo;
-                if (int rc = launch_ln_chain(l, st)) return rc;
+                {
+                    ProfScope ps(ctx, CAT_LN, (blk > 0 ? 12.0 : 8.0) * (double)M * C, st);
+                    if (int rc = launch_ln_chain(l, st)) return rc;
+                }
 
                 GemmArgs g;
                 g.a_hi = w.a_hi; g.a_lo = w.a_lo;
@@ -238,7 +294,11 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
                 AttnParams a;
                 a.qkv = w.qkv; a.out_hi = w.o_hi; a.out_lo = w.o_lo;
                 a.S = Sc; a.F = F; a.J = J; a.C = C; a.temporal = temporal ? 1 : 0; a.scale = 0.f;
-                if (int rc = launch_attention(a, st)) return rc;
+                {
+                    const double L = temporal ? (double)F : (double)J;
+                    ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st);
+                    if (int rc = launch_attention(a, st)) return rc;
+                }
 
                 g.a_hi = w.o_hi; g.a_lo = w.o_lo;
                 g.w_hi = p.wh(b + "attn.proj.weight"); g.w_lo = p.wl(b + "attn.proj.weight");
@@ -248,7 +308,10 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
 
                 l.g0 = l.b0 = nullptr; l.add_f = nullptr;
                 l.g1 = p.w(b + "norm2.weight"); l.b1 = p.w(b + "norm2.bias");
-                if (int rc = launch_ln_chain(l, st)) return rc;
+                {
+                    ProfScope ps(ctx, CAT_LN, 8.0 * (double)M * C, st);
+                    if (int rc = launch_ln_chain(l, st)) return rc;
+                }
 
                 g.a_hi = w.a_hi; g.a_lo = w.a_lo;
                 g.w_hi = p.wh(b + "mlp.fc1.weight"); g.w_lo = p.wl(b + "mlp.fc1.weight");
@@ -271,7 +334,10 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
             h.g1 = p.w("head.0.weight"); h.b1 = p.w("head.0.bias"); h.eps1 = 1e-5f;
             h.wh = p.w("head.1.weight"); h.bh = p.w("head.1.bias");
             h.part_joints = p.joints_dev; h.pred = pred;
-            if (int rc = launch_head(h, st)) return rc;
+            {
+                ProfScope ps(ctx, CAT_EMBED_HEAD, 4.0 * (double)M * C, st);
+                if (int rc = launch_head(h, st)) return rc;
+            }
         }
     }
     return 0;
@@ -437,6 +503,7 @@ int pafuse_ddim_step(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, c
     d.scale = cfg.scale; d.clamp = (float)(1.1 * (double)cfg.scale);
     d.sqrt_recip = sqrt_recip; d.sqrt_recipm1 = sqrt_recipm1; d.c64 = c64;
     d.sqrt_an = sqrt_an; d.c = c; d.sigma = sigma;
+    ProfScope ps(ctx, CAT_DDIM, (flip ? 24.0 : 20.0) * (double)R * cfg.frames * cfg.num_kps * 3, st);
     return launch_ddim_step(d, st);
 }
 
@@ -461,7 +528,10 @@ int pafuse_wb_pose_from_parts(pafuse_ctx* ctx, float* pose, float* out, const in
         if (r >= 0 && !seen) rows.push_back(r);
     }
     PAFUSE_CUDA_OK(cudaMemcpyAsync(ctx->conn_dev, conn_of_joint, nk * sizeof(int), cudaMemcpyHostToDevice, st));
-    if (int rc = launch_reassemble(pose, out, ctx->conn_dev, poses, nk, st)) return rc;
+    {
+        ProfScope ps(ctx, CAT_POST, 8.0 * (double)poses * nk * 3, st);
+        if (int rc = launch_reassemble(pose, out, ctx->conn_dev, poses, nk, st)) return rc;
+    }
     if (mutate_input && !rows.empty()) {
         PAFUSE_CUDA_OK(cudaMemcpyAsync(ctx->conn_rows_dev, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         if (int rc = launch_negate_rows(pose, ctx->conn_rows_dev, (int)rows.size(), poses, nk, st)) return rc;
@@ -493,12 +563,49 @@ int pafuse_aggregate(pafuse_ctx* ctx, const float* pred, const float* traj, cons
     a.B = B; a.K = K; a.H = H; a.F = ctx->cfg.frames; a.J = ctx->cfg.num_kps; a.cam_per_clip = cam_per_clip;
     a.pred = pred; a.traj = traj; a.cam = cam; a.x2d = x2d; a.jagg = jagg; a.pagg = pagg; a.select = select;
     a.reproj = reproj;
+    const double per_pose = 12.0 * a.F * a.J;
+    ProfScope ps(ctx, CAT_POST, per_pose * ((double)B * K * H + 2.0 * B * K), (cudaStream_t)stream);
     return launch_aggregate(a, (cudaStream_t)stream);
 }
 
 int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->debug_simt = enable != 0;
+    return 0;
+}
+
+int pafuse_profile_enable(pafuse_ctx* ctx, int32_t enable) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    Profiler& pr = ctx->prof;
+    for (ProfRec& r : pr.recs) {
+        pr.pool.push_back(r.a);
+        pr.pool.push_back(r.b);
+    }
+    pr.recs.clear();
+    pr.on = enable != 0;
+    return 0;
+}
+
+int pafuse_profile_read(pafuse_ctx* ctx, double* ms, double* work, int64_t* launches, int32_t ncat) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!ms || !work || !launches || ncat < CAT_COUNT) {
+        set_last_error("pafuse_profile_read: need room for %d categories", (int)CAT_COUNT);
+        return PAFUSE_E_ARG;
+    }
+    for (int i = 0; i < ncat; ++i) {
+        ms[i] = 0.0;
+        work[i] = 0.0;
+        launches[i] = 0;
+    }
+    Profiler& pr = ctx->prof;
+    for (ProfRec& r : pr.recs) {
+        PAFUSE_CUDA_OK(cudaEventSynchronize(r.b));
+        float t = 0.f;
+        PAFUSE_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cat] += (double)t;
+        work[r.cat] += r.work;
+        launches[r.cat] += 1;
+    }
     return 0;
 }
 
