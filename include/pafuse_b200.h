@@ -67,7 +67,7 @@ void pafuse_destroy(pafuse_ctx* ctx);
  * (keys/shapes of common/mixste.py:141-210).  `name` is the sub-key after the part,
  * e.g. "STEblocks.3.attn.qkv.weight"; `data` is fp32, host or device (`on_device`).
  * Unknown names return PAFUSE_E_ARG.  Call pafuse_commit_weights once all tensors
- * are set: it derives the bf16 hi/lo operand copies the tensor-core GEMMs read. */
+ * are set: it derives the fp16 hi/lo operand copies the tensor-core GEMMs read. */
 int pafuse_set_weight(pafuse_ctx* ctx, int32_t part, const char* name, const float* data, int64_t numel,
                       int32_t on_device);
 int pafuse_commit_weights(pafuse_ctx* ctx, void* stream);
@@ -125,7 +125,7 @@ int pafuse_profile_read(pafuse_ctx* ctx, double* ms, double* work, int64_t* laun
 
 /* ---- unit-level entry points (tests and profiling; same kernels the path uses) ---- */
 
-/* y = x W^T + b through the tcgen05 bf16x3 GEMM (use_simt != 0: CUDA-core debug reference).
+/* y = x W^T + b through the tcgen05 f16x3 GEMM (use_simt != 0: CUDA-core debug reference).
  * x [M,K] fp32, w [N,K] fp32, b [N]; epilogue 0: y fp32 [M,N]; 1: y = gelu(.) returned as fp32
  * (hi+lo recombined); 2: y += x W^T + b in place. */
 int pafuse_linear(pafuse_ctx* ctx, const float* x, const float* w, const float* b, float* y, int64_t M, int32_t N,
@@ -137,6 +137,8 @@ int pafuse_attention(pafuse_ctx* ctx, const float* qkv, float* out, int32_t S, i
 
 /* debugging switch: route the path's GEMMs through the CUDA-core reference kernel */
 int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable);
+/* process-wide: 2 (default) = tcgen05 CTA pairs (cta_group::2, 256-row tiles), 1 = lone CTAs */
+int pafuse_set_gemm_cta_group(int32_t cta_group);
 
 #ifdef __cplusplus
 }

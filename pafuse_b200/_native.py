@@ -49,6 +49,7 @@ _SIGNATURES = {
                                 c_int32, c_void_p]),
     "pafuse_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "pafuse_set_debug_simt_gemm": (c_int32, [c_void_p, c_int32]),
+    "pafuse_set_gemm_cta_group": (c_int32, [c_int32]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -253,6 +254,10 @@ class NativeContext:
         with torch.cuda.device(self.device):
             check(self.lib.pafuse_profile_read(self.handle, ms, work, cnt, n), "pafuse_profile_read")
         return {name: (ms[i], work[i], int(cnt[i])) for i, name in enumerate(self.PROFILE_CATEGORIES)}
+
+    def set_gemm_cta_group(self, cta_group: int):
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_set_gemm_cta_group(int(cta_group)), "pafuse_set_gemm_cta_group")
 
     def launch_count(self) -> int:
         return int(self.lib.pafuse_launch_count())

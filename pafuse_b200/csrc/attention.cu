@@ -8,7 +8,7 @@
 // shared memory with coalesced 16-byte loads; thread (head, query row) keeps its
 // q row and output row in registers and streams over the keys with an online
 // softmax (4 keys per step, one rescale per step), reading K/V as warp-broadcast
-// LDS.128.  The output is written as the bf16 hi/lo pair the proj GEMM consumes.
+// LDS.128.  The output is written as the fp16 hi/lo pair the proj GEMM consumes.
 // Only 3.3 % of the path's FLOPs live here.
 #include "kernels.cuh"
 

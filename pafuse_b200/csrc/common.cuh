@@ -1,9 +1,10 @@
-// Shared device helpers for the sm_100a kernels: error plumbing, bf16 hi/lo
+// Shared device helpers for the sm_100a kernels: error plumbing, fp16 hi/lo
 // splitting, and thin inline-PTX wrappers for mbarrier / TMA / tcgen05.
 #pragma once
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -35,26 +36,39 @@ extern thread_local long long g_launch_count;  // kernels launched by this libra
         }                                                                                 \
     } while (0)
 
-// ---------------------------------------------------------------- bf16 split
-// v ~= hi + lo with hi = bf16(v), lo = bf16(v - hi): 16 significant bits.
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+// ---------------------------------------------------------------- fp16 hi/lo split
+// Tensor-core operand format of the whole path ("f16x3"): an fp32 value v is carried as
+//   hi = fp16(v), lo = fp16(v - hi)      ->  hi + lo keeps ~22 significant bits,
+// and a product a*w is evaluated as a_lo*w_hi + a_hi*w_lo + a_hi*w_hi (3 tensor-core passes,
+// fp32 accumulation); the dropped lo*lo term is ~2^-22 relative.  fp16 (11-bit significand) is
+// used instead of bf16 (8-bit) because both run at the same tcgen05 rate and the pair is 64x
+// more precise; its narrow range is handled by (a) saturating the conversion and (b) storing
+// GEMM weights pre-multiplied by WEIGHT_SCALE (a power of two, undone exactly in the epilogue)
+// so that the lo halves of typical |w| ~ 1e-2 stay out of the fp16 subnormal range.
+typedef __half op_t;
+constexpr float WEIGHT_SCALE = 256.0f;
+constexpr float WEIGHT_UNSCALE = 1.0f / 256.0f;
+
+__device__ __forceinline__ void split_op(float v, op_t& hi, op_t& lo) {
+    v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+__device__ __forceinline__ float join_op(op_t hi, op_t lo) { return __half2float(hi) + __half2float(lo); }
+
+__device__ __forceinline__ uint32_t pack_op2(op_t a, op_t b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
-    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-
-// split 4 floats, produce 2x uint2 (hi, lo) of packed bf16
+// split 4 floats, produce 2x uint2 (hi, lo) of packed fp16
 __device__ __forceinline__ void split4(const float v[4], uint2& hi, uint2& lo) {
-    __nv_bfloat16 h[4], l[4];
+    op_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split_bf16(v[i], h[i], l[i]);
-    hi.x = pack_bf16x2(h[0], h[1]);
-    hi.y = pack_bf16x2(h[2], h[3]);
-    lo.x = pack_bf16x2(l[0], l[1]);
-    lo.y = pack_bf16x2(l[2], l[3]);
+    for (int i = 0; i < 4; ++i) split_op(v[i], h[i], l[i]);
+    hi.x = pack_op2(h[0], h[1]);
+    hi.y = pack_op2(h[2], h[3]);
+    lo.x = pack_op2(l[0], l[1]);
+    lo.y = pack_op2(l[2], l[3]);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {  // nn.GELU() default (exact erf form)
@@ -139,32 +153,90 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-// ---------------------------------------------------------------- PTX: tcgen05
+// ---------------------------------------------------------------- PTX: cluster
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(smem_u32(bar)), "r"(rank)
+        : "memory");
+}
+// 2-CTA TMA load: data lands in THIS CTA's smem, the transaction bytes are counted on the
+// mbarrier of the pair's even CTA (peer bit 24 of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// ---------------------------------------------------------------- PTX: tcgen05 (CG = cta_group, 1 or 2)
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    if (CG == 1)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    else
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_relinquish() {
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1)
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    else
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    if (CG == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate, issued by ONE thread
-__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+// D[tmem] (+)= A[smem desc] * B[smem desc], 16-bit inputs, fp32 accumulate, issued by ONE thread
+// (of the pair's even CTA when CG == 2: the instruction then reads both CTAs' shared memory at
+// the same offsets and writes both CTAs' tensor memory).
+template <int CG>
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (CG == 1)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
-// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+// arrive on an mbarrier (same smem offset in every CTA of the group) once all previously issued
+// MMAs of this thread have completed
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    if (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> lane base+i)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t r[32]) {
@@ -192,11 +264,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
     return d;
 }
 
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both operands K-major.
+// M is the instruction's M (128 for cta_group::1, 256 for cta_group::2).
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
     return (1u << 4)          // D format: f32
-           | (1u << 7)        // A format: bf16
-           | (1u << 10)       // B format: bf16
+           | (0u << 7)        // A format: f16
+           | (0u << 10)       // B format: f16
            | ((N >> 3) << 17) // N, 3 LSBs dropped
            | ((M >> 4) << 24);// M, 4 LSBs dropped
 }

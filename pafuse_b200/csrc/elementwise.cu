@@ -9,19 +9,19 @@
 namespace pafuse {
 
 // ------------------------------------------------------------------ weight split
-__global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
-                                     __nv_bfloat16* __restrict__ lo, size_t n) {
+__global__ void split_weights_kernel(const float* __restrict__ w, op_t* __restrict__ hi,
+                                     op_t* __restrict__ lo, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        __nv_bfloat16 h, l;
-        split_bf16(w[i], h, l);
+        op_t h, l;
+        split_op(w[i] * WEIGHT_SCALE, h, l);           // exact power-of-two pre-scale, undone in the GEMM epilogue
         hi[i] = h;
         lo[i] = l;
     }
 }
 
-int launch_split_weights(const float* w, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st) {
+int launch_split_weights(const float* w, op_t* hi, op_t* lo, size_t n, cudaStream_t st) {
     if (n == 0) return 0;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -123,11 +123,11 @@ int launch_embed(const EmbedParams& p, cudaStream_t st) {
     return 0;
 }
 
-// ------------------------------------------------------------------ LayerNorm (+ chained norm) + bf16 split
+// ------------------------------------------------------------------ LayerNorm (+ chained norm) + fp16 split
 // Optional first stage (g0 != nullptr):  x <- LN(x; g0,b0,eps0) [+ add_f[f,:]]   written back (residual stream)
 //     = the shared Spatial_norm / Temporal_norm after every block (mixste.py:243,257,269,273)
 //       and the Temporal_pos_embed add before TTE block 0 (:250).
-// Second stage (g1 != nullptr):         a  = LN(x; g1,b1,eps1) -> bf16 hi/lo     (norm1 / norm2 of the next GEMM)
+// Second stage (g1 != nullptr):         a  = LN(x; g1,b1,eps1) -> fp16 hi/lo     (norm1 / norm2 of the next GEMM)
 // One warp per row, row kept in registers (C <= 32*MAXV).
 template <int MAXV>
 __global__ void ln_chain_kernel(LnParams p) {
@@ -186,15 +186,15 @@ __global__ void ln_chain_kernel(LnParams p) {
             q += d * d;
         }
         float rstd = (1.0f / sqrtf(warp_sum(q) * invC + p.eps1));
-        __nv_bfloat16* oh = p.out_hi + (size_t)m * C;
-        __nv_bfloat16* ol = p.out_lo + (size_t)m * C;
+        op_t* oh = p.out_hi + (size_t)m * C;
+        op_t* ol = p.out_lo + (size_t)m * C;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             int c = lane + 32 * i;
             if (c < C) {
                 float y = (v[i] - mean) * rstd * p.g1[c] + p.b1[c];
-                __nv_bfloat16 h, l;
-                split_bf16(y, h, l);
+                op_t h, l;
+                split_op(y, h, l);
                 oh[c] = h;
                 ol[c] = l;
             }

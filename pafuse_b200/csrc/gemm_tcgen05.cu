@@ -1,17 +1,21 @@
 // Token-wise linear layers of the STE/TTE blocks (mixste.py:65,80,38-41) on the
 // sm_100a tensor cores:  D[M,N] = A[M,K] * W[N,K]^T + bias, fp32 accumulation in TMEM.
 //
-// Precision: "bf16x3".  Every fp32 operand v is carried as the pair
-// (hi, lo) = (bf16(v), bf16(v - hi)) and the product is evaluated as
-//     A_hi*W_hi + A_hi*W_lo + A_lo*W_hi          (3 tcgen05.mma per K-slice)
-// which keeps ~16 significant bits per operand (error ~2^-17 per product, about
-// 50x tighter than single-pass TF32) at 3 bf16 MMAs per slice instead of the 6
-// bf16-equivalents of a 3xTF32 scheme.  Plain TF32/BF16 do not meet the path's
-// tolerance.
+// Precision: "f16x3".  Every fp32 operand v is carried as the pair
+// (hi, lo) = (fp16(v), fp16(v - hi)) and the product is evaluated as
+//     A_lo*W_hi + A_hi*W_lo + A_hi*W_hi          (3 tcgen05.mma per K-slice)
+// (~22 significant bits per operand; plain TF32/BF16 do not meet the path's
+// tolerance).  Weights are stored pre-scaled by 2^8 (common.cuh).
 //
-// Structure: persistent warp-specialised CTA, one per SM.
+// Structure: persistent, warp-specialised, one CTA per SM; with CG == 2 the two CTAs
+// of a cluster form a tcgen05 CTA pair that owns a 256 x BN output tile: each CTA
+// TMA-loads its own 128 rows of A and HALF of the W tile (BN/2 rows), the even CTA
+// issues cta_group::2 MMAs that read both shared memories and write both tensor
+// memories.  Per byte fetched from L2 the pair does twice the math of a lone CTA --
+// the 1-CTA version of this kernel was L2->SMEM bound at 42 % tensor utilisation
+// (profiles/r1_gemm_1cta.txt).
 //   warp 0    TMA producer: 4 tiled loads per stage (A_hi, A_lo, W_hi, W_lo; 128B swizzle)
-//   warp 1    MMA issuer: one lane issues 3 x (BK/16) tcgen05.mma per stage, commits to mbarriers
+//   warp 1    MMA issuer (even CTA only): 3 x (BK/16) tcgen05.mma per stage, commits to mbarriers
 //   warp 2    TMEM allocator (512 columns = two BN<=256 accumulator buffers)
 //   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns, bias / GELU+split / residual, global stores
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue),
@@ -20,15 +24,16 @@
 
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace pafuse {
 
 namespace {
 
-constexpr int BM = 128;              // rows per tile = UMMA M
-constexpr int BK = 64;               // K slice per stage = one 128-byte swizzle span of bf16
-constexpr int UK = 16;               // K per tcgen05.mma (bf16)
-constexpr int MAX_STAGES = 4;
+constexpr int BM = 128;              // rows per CTA = TMEM lanes
+constexpr int BK = 64;               // K slice per stage = one 128-byte swizzle span of fp16
+constexpr int UK = 16;               // K per tcgen05.mma (16-bit operands)
+constexpr int MAX_STAGES = 6;
 constexpr int A_TILE_BYTES = BM * BK * 2;           // 16 KiB
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NUM_THREADS = 256;
@@ -38,21 +43,22 @@ constexpr int TMEM_COLS = 512;
 struct KernelParams {
     long long M;
     int N, K;
-    int block_n;
-    int m_tiles, n_tiles;
+    int block_n;                     // output tile width (UMMA N)
+    int m_tiles, n_tiles;            // tiles of (BM*CG) x block_n
     int stages;
-    int stage_bytes;
+    int stage_bytes;                 // per CTA
+    float out_scale;                 // undoes WEIGHT_SCALE
     const float* bias;
     float* out_f32;
-    __nv_bfloat16* out_hi;
-    __nv_bfloat16* out_lo;
+    op_t* out_hi;
+    op_t* out_lo;
 };
 
-template <int EPI>
+template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                   const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-                   const KernelParams p) {
+gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                  const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                  const KernelParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -65,10 +71,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
     const int BN = p.block_n;
-    const int w_tile_bytes = BN * BK * 2;
+    const int WN = BN / CG;                                   // W rows this CTA loads per stage
+    const int w_tile_bytes = WN * BK * 2;
     const int num_kb = (p.K + BK - 1) / BK;
     const int num_tiles = p.m_tiles * p.n_tiles;
+    const int group = blockIdx.x / CG;                        // CTA pair (or CTA) index
+    const int num_groups = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tm_a_hi);
@@ -78,40 +89,51 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&full_bar[s], 1);                       // the leader's arrive.expect_tx
+            mbar_init(&empty_bar[s], 1);                      // one tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 128);
+            mbar_init(&tmem_full_bar[a], 1);                  // one tcgen05.commit
+            mbar_init(&tmem_empty_bar[a], 4 * CG);            // one elected lane per epilogue warp of every CTA of the group
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(&tmem_base_slot, TMEM_COLS);
-        tmem_relinquish();
+        tmem_alloc<CG>(&tmem_base_slot, TMEM_COLS);
+        tmem_relinquish<CG>();
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();    // peers' barriers are initialised past this point
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (every CTA loads its own operands) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = group; tile < num_tiles; tile += num_groups) {
                 const int m_tile = tile / p.n_tiles;
                 const int n_tile = tile % p.n_tiles;
+                const int m0 = (m_tile * CG + (int)cta_rank) * BM;
+                const int n0 = n_tile * BN + (int)cta_rank * WN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);  // MMAs that read this stage (in both CTAs) have retired
                     uint8_t* st = smem + (size_t)stage * p.stage_bytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
-                    tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BK, m_tile * BM);
-                    tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m_tile * BM);
-                    tma_load_2d(st + 2 * A_TILE_BYTES, &tm_w_hi, &full_bar[stage], kb * BK, n_tile * BN);
-                    tma_load_2d(st + 2 * A_TILE_BYTES + w_tile_bytes, &tm_w_lo, &full_bar[stage], kb * BK, n_tile * BN);
+                    if (CG == 1) {
+                        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
+                        tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
+                        tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m0);
+                        tma_load_2d(st + 2 * A_TILE_BYTES, &tm_w_hi, &full_bar[stage], kb * BK, n0);
+                        tma_load_2d(st + 2 * A_TILE_BYTES + w_tile_bytes, &tm_w_lo, &full_bar[stage], kb * BK, n0);
+                    } else {
+                        // both CTAs' bytes are counted on the leader's barrier
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 * p.stage_bytes));
+                        tma_load_2d_pair(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
+                        tma_load_2d_pair(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m0);
+                        tma_load_2d_pair(st + 2 * A_TILE_BYTES, &tm_w_hi, &full_bar[stage], kb * BK, n0);
+                        tma_load_2d_pair(st + 2 * A_TILE_BYTES + w_tile_bytes, &tm_w_lo, &full_bar[stage], kb * BK, n0);
+                    }
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;
@@ -120,19 +142,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(BM, (uint32_t)BN);
+        // ===================== MMA issuer (one thread of the group's even CTA) =====================
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc_f16((uint32_t)(BM * CG), (uint32_t)BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // epilogue has drained this buffer
+            for (int tile = group; tile < num_tiles; tile += num_groups) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // every epilogue warp of the group drained this buffer
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);               // operands landed
+                    mbar_wait(&full_bar[stage], phase);               // operands landed (in both CTAs)
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
                     const uint32_t a_hi = sa, a_lo = sa + A_TILE_BYTES;
@@ -145,12 +167,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         const uint64_t dal = make_smem_desc_sw128(a_lo + koff);
                         const uint64_t dwh = make_smem_desc_sw128(w_hi + koff);
                         const uint64_t dwl = make_smem_desc_sw128(w_lo + koff);
-                        umma_bf16_ss(d_tmem, dal, dwh, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
-                        umma_bf16_ss(d_tmem, dah, dwl, idesc, 1u);
-                        umma_bf16_ss(d_tmem, dah, dwh, idesc, 1u);
+                        umma_f16_ss<CG>(d_tmem, dal, dwh, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
+                        umma_f16_ss<CG>(d_tmem, dah, dwl, idesc, 1u);
+                        umma_f16_ss<CG>(d_tmem, dah, dwh, idesc, 1u);
                     }
-                    umma_commit(&empty_bar[stage]);                   // frees the smem stage when the MMAs retire
-                    if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+                    umma_commit<CG>(&empty_bar[stage]);               // frees the stage (in both CTAs) when the MMAs retire
+                    if (kb == num_kb - 1) umma_commit<CG>(&tmem_full_bar[acc]);
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;
@@ -161,16 +183,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
         }
     } else if (warp >= EPI_WARP0) {
-        // ===================== epilogue =====================
+        // ===================== epilogue (every CTA drains its own 128 accumulator rows) =====================
         const int q = warp - EPI_WARP0;                               // TMEM lane quarter == warp % 4
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const float oscale = p.out_scale;
+        for (int tile = group; tile < num_tiles; tile += num_groups) {
             const int m_tile = tile / p.n_tiles;
             const int n_tile = tile % p.n_tiles;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
-            const long long row = (long long)m_tile * BM + q * 32 + lane;
+            const long long row = (long long)(m_tile * CG + (int)cta_rank) * BM + q * 32 + lane;
             const bool row_ok = row < p.M;
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
             for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -186,10 +209,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         for (int i = 0; i < 8; ++i) {
                             float4 bb = __ldg(b4 + i);
                             float4 v;
-                            v.x = __uint_as_float(r[4 * i + 0]) + bb.x;
-                            v.y = __uint_as_float(r[4 * i + 1]) + bb.y;
-                            v.z = __uint_as_float(r[4 * i + 2]) + bb.z;
-                            v.w = __uint_as_float(r[4 * i + 3]) + bb.w;
+                            v.x = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bb.x);
+                            v.y = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bb.y);
+                            v.z = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bb.z);
+                            v.w = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bb.w);
                             if (EPI == EPI_RESID) {
                                 float4 x = o4[i];
                                 v.x += x.x;
@@ -206,10 +229,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                         for (int i = 0; i < 8; ++i) {
                             float4 bb = __ldg(b4 + i);
                             float v[4];
-                            v[0] = gelu_erf(__uint_as_float(r[4 * i + 0]) + bb.x);
-                            v[1] = gelu_erf(__uint_as_float(r[4 * i + 1]) + bb.y);
-                            v[2] = gelu_erf(__uint_as_float(r[4 * i + 2]) + bb.z);
-                            v[3] = gelu_erf(__uint_as_float(r[4 * i + 3]) + bb.w);
+                            v[0] = gelu_erf(fmaf(__uint_as_float(r[4 * i + 0]), oscale, bb.x));
+                            v[1] = gelu_erf(fmaf(__uint_as_float(r[4 * i + 1]), oscale, bb.y));
+                            v[2] = gelu_erf(fmaf(__uint_as_float(r[4 * i + 2]), oscale, bb.z));
+                            v[3] = gelu_erf(fmaf(__uint_as_float(r[4 * i + 3]), oscale, bb.w));
                             uint2 hi, lo;
                             split4(v, hi, lo);
                             oh[i] = hi;
@@ -219,29 +242,33 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 }
             }
             tcgen05_fence_before();
-            mbar_arrive(&tmem_empty_bar[acc]);                        // 128 arrivals release the buffer
+            __syncwarp();
+            if (lane == 0) {                                          // 4*CG arrivals release the buffer to the issuer
+                if (CG == 1) mbar_arrive(&tmem_empty_bar[acc]);
+                else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();            // nobody leaves while the peer may still signal it
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc<CG>(tmem_base, TMEM_COLS);
     }
 }
 
 // ------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
-int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, int K, int box_rows) {
+int make_map_f16(CUtensorMap* map, const void* ptr, long long rows, int K, int box_rows) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -253,27 +280,82 @@ int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, int K, int 
 }
 
 int g_num_sms = 0;
+int g_force_cg = 0;      // PAFUSE_GEMM_CTA_GROUP=1|2 overrides the default (2)
 
-template <int EPI>
+template <int EPI, int CG>
 int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
                const KernelParams& kp, int grid, int smem, cudaStream_t st) {
-    auto kern = gemm_bf16x3_kernel<EPI>;
-    static int configured_smem = 0;
-    if (configured_smem < smem) {
-        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 2048));
-        configured_smem = SMEM_LIMIT;
+    auto kern = gemm_f16x3_kernel<EPI, CG>;
+    static bool configured = false;                                   // per template instance
+    if (!configured) {
+        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024));
+        configured = true;
     }
-    kern<<<grid, NUM_THREADS, smem, st>>>(ah, al, wh, wl, kp);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PAFUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ah, al, wh, wl, kp));
     PAFUSE_LAUNCH_OK();
     return 0;
+}
+
+template <int CG>
+int launch_cg(const GemmArgs& g, cudaStream_t st) {
+    const int BN = gemm_pick_block_n(g.N);
+    if (BN < 32 || BN % 32 != 0 || g.K % 8 != 0 || g.N % 8 != 0) {
+        set_last_error("gemm: unsupported shape N=%d K=%d (block_n=%d)", g.N, g.K, BN);
+        return -1;
+    }
+    CUtensorMap ah, al, wh, wl;
+    if (int rc = make_map_f16(&ah, g.a_hi, g.M, g.K, BM)) return rc;
+    if (int rc = make_map_f16(&al, g.a_lo, g.M, g.K, BM)) return rc;
+    if (int rc = make_map_f16(&wh, g.w_hi, g.N, g.K, BN / CG)) return rc;
+    if (int rc = make_map_f16(&wl, g.w_lo, g.N, g.K, BN / CG)) return rc;
+
+    KernelParams kp;
+    kp.M = g.M;
+    kp.N = g.N;
+    kp.K = g.K;
+    kp.block_n = BN;
+    kp.m_tiles = (int)((g.M + BM * CG - 1) / (BM * CG));
+    kp.n_tiles = g.N / BN;
+    kp.stage_bytes = 2 * A_TILE_BYTES + 2 * (BN / CG) * BK * 2;
+    int stages = (SMEM_LIMIT - 2048 - 1024) / kp.stage_bytes;         // 1 KiB alignment slack + static barriers
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    kp.stages = stages;
+    kp.out_scale = g.out_scale;
+    kp.bias = g.bias;
+    kp.out_f32 = g.out_f32;
+    kp.out_hi = g.out_hi;
+    kp.out_lo = g.out_lo;
+    const int smem = stages * kp.stage_bytes + 1024;
+    const long long tiles = (long long)kp.m_tiles * kp.n_tiles;
+    const int max_groups = g_num_sms / CG;
+    const int grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;
+    switch (g.epilogue) {
+        case EPI_F32: return launch_epi<EPI_F32, CG>(ah, al, wh, wl, kp, grid, smem, st);
+        case EPI_GELU_SPLIT: return launch_epi<EPI_GELU_SPLIT, CG>(ah, al, wh, wl, kp, grid, smem, st);
+        case EPI_RESID: return launch_epi<EPI_RESID, CG>(ah, al, wh, wl, kp, grid, smem, st);
+    }
+    set_last_error("gemm: bad epilogue %d", g.epilogue);
+    return -1;
 }
 
 }  // namespace
 
 int gemm_pick_block_n(int N) {
-    // largest UMMA-legal N (multiple of 16, <= 256) that divides the layer width; the
+    // largest UMMA-legal N (multiple of 32 here, <= 256) that divides the layer width; the
     // path's widths are 224/256/384/448/512/672/768/1152 -> 224/256/192/224/256/224/256/192
-    for (int bn = 256; bn >= 16; bn -= 16)
+    for (int bn = 256; bn >= 32; bn -= 32)
         if (N % bn == 0) return bn;
     return 0;
 }
@@ -291,78 +373,43 @@ int gemm_init() {
     int dev = 0;
     PAFUSE_CUDA_OK(cudaGetDevice(&dev));
     PAFUSE_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const char* e = getenv("PAFUSE_GEMM_CTA_GROUP");
+    g_force_cg = e ? atoi(e) : 0;
     return 0;
 }
+
+void gemm_set_cta_group(int cg) { g_force_cg = cg; }
 
 int launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t st) {
     if (g.M == 0) return 0;
     if (int rc = gemm_init()) return rc;
-    const int BN = gemm_pick_block_n(g.N);
-    if (BN < 32 || BN % 32 != 0 || g.K % 8 != 0 || g.N % 8 != 0) {
-        set_last_error("gemm: unsupported shape N=%d K=%d (block_n=%d)", g.N, g.K, BN);
-        return -1;
-    }
-    CUtensorMap ah, al, wh, wl;
-    if (int rc = make_map_bf16(&ah, g.a_hi, g.M, g.K, BM)) return rc;
-    if (int rc = make_map_bf16(&al, g.a_lo, g.M, g.K, BM)) return rc;
-    if (int rc = make_map_bf16(&wh, g.w_hi, g.N, g.K, BN)) return rc;
-    if (int rc = make_map_bf16(&wl, g.w_lo, g.N, g.K, BN)) return rc;
-
-    KernelParams kp;
-    kp.M = g.M;
-    kp.N = g.N;
-    kp.K = g.K;
-    kp.block_n = BN;
-    kp.m_tiles = (int)((g.M + BM - 1) / BM);
-    kp.n_tiles = g.N / BN;
-    kp.stage_bytes = 2 * A_TILE_BYTES + 2 * BN * BK * 2;
-    int stages = (SMEM_LIMIT - 4096) / kp.stage_bytes;
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    kp.stages = stages;
-    kp.bias = g.bias;
-    kp.out_f32 = g.out_f32;
-    kp.out_hi = g.out_hi;
-    kp.out_lo = g.out_lo;
-    const int smem = stages * kp.stage_bytes + 1024;
-    const long long tiles = (long long)kp.m_tiles * kp.n_tiles;
-    const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-    switch (g.epilogue) {
-        case EPI_F32: return launch_epi<EPI_F32>(ah, al, wh, wl, kp, grid, smem, st);
-        case EPI_GELU_SPLIT: return launch_epi<EPI_GELU_SPLIT>(ah, al, wh, wl, kp, grid, smem, st);
-        case EPI_RESID: return launch_epi<EPI_RESID>(ah, al, wh, wl, kp, grid, smem, st);
-    }
-    set_last_error("gemm: bad epilogue %d", g.epilogue);
-    return -1;
+    return g_force_cg == 1 ? launch_cg<1>(g, st) : launch_cg<2>(g, st);
 }
 
 // ------------------------------------------------------------------ debug reference on CUDA cores
 // Same contract, evaluated as (A_hi+A_lo)*(W_hi+W_lo) in fp32 FMAs: used by the unit
-// tests to check the tensor-core kernel on device and selectable for bisecting
-// (PAFUSE_DEBUG_SIMT_GEMM=1).  Not a production path.
+// tests to check the tensor-core kernel on device and selectable for bisecting.
+// Not a production path.
 __global__ void gemm_simt_kernel(GemmArgs g) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= g.M * g.N) return;
     long long m = idx / g.N;
     int n = (int)(idx % g.N);
-    const __nv_bfloat16* ah = g.a_hi + (size_t)m * g.K;
-    const __nv_bfloat16* al = g.a_lo + (size_t)m * g.K;
-    const __nv_bfloat16* wh = g.w_hi + (size_t)n * g.K;
-    const __nv_bfloat16* wl = g.w_lo + (size_t)n * g.K;
+    const op_t* ah = g.a_hi + (size_t)m * g.K;
+    const op_t* al = g.a_lo + (size_t)m * g.K;
+    const op_t* wh = g.w_hi + (size_t)n * g.K;
+    const op_t* wl = g.w_lo + (size_t)n * g.K;
     float acc = 0.f;
-    for (int k = 0; k < g.K; ++k) {
-        float a = __bfloat162float(ah[k]) + __bfloat162float(al[k]);
-        float w = __bfloat162float(wh[k]) + __bfloat162float(wl[k]);
-        acc = fmaf(a, w, acc);
-    }
-    float v = acc + g.bias[n];
+    for (int k = 0; k < g.K; ++k) acc = fmaf(join_op(ah[k], al[k]), join_op(wh[k], wl[k]), acc);
+    float v = fmaf(acc, g.out_scale, g.bias[n]);
     size_t o = (size_t)m * g.N + n;
     if (g.epilogue == EPI_F32) {
         g.out_f32[o] = v;
     } else if (g.epilogue == EPI_RESID) {
         g.out_f32[o] += v;
     } else {
-        __nv_bfloat16 h, l;
-        split_bf16(gelu_erf(v), h, l);
+        op_t h, l;
+        split_op(gelu_erf(v), h, l);
         g.out_hi[o] = h;
         g.out_lo[o] = l;
     }

@@ -31,9 +31,9 @@ struct LnParams {
     const float *g0, *b0;     // optional shared norm written back to x
     float eps0;
     const float* add_f;       // optional [F,C] added after the first norm (Temporal_pos_embed)
-    const float *g1, *b1;     // optional second norm -> bf16 hi/lo
+    const float *g1, *b1;     // optional second norm -> fp16 hi/lo
     float eps1;
-    __nv_bfloat16 *out_hi, *out_lo;
+    op_t *out_hi, *out_lo;
 };
 
 struct HeadParams {
@@ -80,7 +80,7 @@ struct AggParams {
 
 struct AttnParams {
     const float* qkv;         // [M,3C]
-    __nv_bfloat16 *out_hi, *out_lo;  // [M,C]
+    op_t *out_hi, *out_lo;  // [M,C]
     int S, F, J, C;
     int temporal;             // 0: attend over J inside (s,f); 1: over F inside (s,j)
     float scale;              // head_dim^-0.5, set by launch_attention
@@ -89,17 +89,18 @@ struct AttnParams {
 enum GemmEpilogue { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_RESID = 2 };
 
 struct GemmArgs {
-    const __nv_bfloat16 *a_hi, *a_lo;   // [M,K]
-    const __nv_bfloat16 *w_hi, *w_lo;   // [N,K]
+    const op_t *a_hi, *a_lo;   // [M,K]
+    const op_t *w_hi, *w_lo;   // [N,K]
     const float* bias;                  // [N]
     float* out_f32;                     // [M,N]  (EPI_F32: written; EPI_RESID: out += acc + bias)
-    __nv_bfloat16 *out_hi, *out_lo;     // [M,N]  (EPI_GELU_SPLIT)
+    op_t *out_hi, *out_lo;     // [M,N]  (EPI_GELU_SPLIT)
     long long M;
     int N, K;
     int epilogue;
+    float out_scale = WEIGHT_UNSCALE;   // accumulator scale applied before the bias (weights are stored pre-scaled)
 };
 
-int launch_split_weights(const float* w, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
+int launch_split_weights(const float* w, op_t* hi, op_t* lo, size_t n, cudaStream_t st);
 int launch_time_mlp(const float* sinus, const float* w1, const float* b1, const float* w2, const float* b2,
                     float* temb, int C, cudaStream_t st);
 int launch_embed(const EmbedParams& p, cudaStream_t st);
@@ -114,10 +115,11 @@ int launch_project(const float* X, const float* cam, float* out, long long npts,
 int launch_aggregate(const AggParams& p, cudaStream_t st);
 int launch_attention(const AttnParams& p, cudaStream_t st);
 
-// tcgen05 GEMM (bf16x3 split precision).  Tensor maps are built per call from the raw pointers.
+// tcgen05 GEMM (f16x3 split precision).  Tensor maps are built per call from the raw pointers.
 int gemm_init();                                            // resolves cuTensorMapEncodeTiled
 int launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);   // debug reference (CUDA cores)
 int gemm_pick_block_n(int N);
+void gemm_set_cta_group(int cg);                            // 1: lone CTAs, 2 (default): tcgen05 CTA pairs
 
 }  // namespace pafuse

@@ -27,7 +27,7 @@ void set_last_error(const char* fmt, ...) {
 struct Slot {
     size_t off = 0;      // element offset inside the part arena
     size_t numel = 0;
-    bool gemm = false;   // needs a bf16 hi/lo copy
+    bool gemm = false;   // needs a fp16 hi/lo copy
     bool set = false;
 };
 
@@ -36,23 +36,23 @@ struct Part {
     std::map<std::string, Slot> slots;
     size_t total = 0;
     float* f32 = nullptr;
-    __nv_bfloat16* hi = nullptr;
-    __nv_bfloat16* lo = nullptr;
+    op_t* hi = nullptr;
+    op_t* lo = nullptr;
     int* joints_dev = nullptr;
     float* temb = nullptr;
 
     const float* w(const std::string& n) const { return f32 + slots.at(n).off; }
-    const __nv_bfloat16* wh(const std::string& n) const { return hi + slots.at(n).off; }
-    const __nv_bfloat16* wl(const std::string& n) const { return lo + slots.at(n).off; }
+    const op_t* wh(const std::string& n) const { return hi + slots.at(n).off; }
+    const op_t* wl(const std::string& n) const { return lo + slots.at(n).off; }
 };
 
 struct Workspace {
     long long rows_x_c = 0;   // capacity in (rows * C) units
     float* x = nullptr;
-    __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr;
+    op_t *a_hi = nullptr, *a_lo = nullptr;
     float* qkv = nullptr;
-    __nv_bfloat16 *o_hi = nullptr, *o_lo = nullptr;
-    __nv_bfloat16 *h_hi = nullptr, *h_lo = nullptr;
+    op_t *o_hi = nullptr, *o_lo = nullptr;
+    op_t *h_hi = nullptr, *h_lo = nullptr;
 };
 
 // Optional per-launch device timing (bench.py's roofline leg): CUDA events on the launching
@@ -356,7 +356,7 @@ bool check_ctx(pafuse_ctx* ctx) {
 extern "C" {
 
 const char* pafuse_last_error(void) { return g_err; }
-const char* pafuse_version(void) { return "pafuse_b200 0.1 (sm_100a, tcgen05 bf16x3)"; }
+const char* pafuse_version(void) { return "pafuse_b200 0.2 (sm_100a, tcgen05 f16x3, cta_group::2)"; }
 int64_t pafuse_launch_count(void) { return (int64_t)g_launch_count; }
 
 int pafuse_create(const pafuse_config* cfg, pafuse_ctx** out) {
@@ -574,6 +574,16 @@ int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable) {
     return 0;
 }
 
+int pafuse_set_gemm_cta_group(int32_t cta_group) {
+    if (cta_group != 1 && cta_group != 2) {
+        set_last_error("pafuse_set_gemm_cta_group: cta_group must be 1 or 2");
+        return PAFUSE_E_ARG;
+    }
+    if (int rc = gemm_init()) return rc;
+    gemm_set_cta_group(cta_group);
+    return 0;
+}
+
 int pafuse_profile_enable(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     Profiler& pr = ctx->prof;
@@ -611,13 +621,13 @@ int pafuse_profile_read(pafuse_ctx* ctx, double* ms, double* work, int64_t* laun
 
 // ---- unit-level entry points -------------------------------------------------------------
 
-__global__ void split_rows_kernel(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n) {
+__global__ void split_rows_kernel(const float* x, op_t* hi, op_t* lo, size_t n, float scale) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) split_bf16(x[i], hi[i], lo[i]);
+    if (i < n) split_op(x[i] * scale, hi[i], lo[i]);
 }
-__global__ void join_rows_kernel(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* y, size_t n) {
+__global__ void join_rows_kernel(const op_t* hi, const op_t* lo, float* y, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+    if (i < n) y[i] = join_op(hi[i], lo[i]);
 }
 
 int pafuse_linear(pafuse_ctx* ctx, const float* x, const float* w, const float* b, float* y, int64_t M, int32_t N,
@@ -628,14 +638,14 @@ int pafuse_linear(pafuse_ctx* ctx, const float* x, const float* w, const float* 
         return PAFUSE_E_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    __nv_bfloat16 *xh = nullptr, *xl = nullptr, *wh = nullptr, *wl = nullptr, *yh = nullptr, *yl = nullptr;
+    op_t *xh = nullptr, *xl = nullptr, *wh = nullptr, *wl = nullptr, *yh = nullptr, *yl = nullptr;
     size_t nx = (size_t)M * K, nw = (size_t)N * K, ny = (size_t)M * N;
     int rc = 0;
     if (dev_alloc(&xh, nx) || dev_alloc(&xl, nx) || dev_alloc(&wh, nw) || dev_alloc(&wl, nw)) rc = PAFUSE_E_CUDA;
     if (!rc && epilogue == EPI_GELU_SPLIT && (dev_alloc(&yh, ny) || dev_alloc(&yl, ny))) rc = PAFUSE_E_CUDA;
     if (!rc) {
-        split_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(x, xh, xl, nx);
-        split_rows_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, wh, wl, nw);
+        split_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(x, xh, xl, nx, 1.0f);
+        split_rows_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, wh, wl, nw, WEIGHT_SCALE);
         GemmArgs g;
         g.a_hi = xh; g.a_lo = xl; g.w_hi = wh; g.w_lo = wl; g.bias = b; g.out_f32 = y; g.out_hi = yh; g.out_lo = yl;
         g.M = M; g.N = N; g.K = K; g.epilogue = epilogue;
@@ -660,7 +670,7 @@ int pafuse_attention(pafuse_ctx* ctx, const float* qkv, float* out, int32_t S, i
     }
     cudaStream_t st = (cudaStream_t)stream;
     size_t n = (size_t)S * ctx->cfg.frames * J * C;
-    __nv_bfloat16 *oh = nullptr, *ol = nullptr;
+    op_t *oh = nullptr, *ol = nullptr;
     int rc = 0;
     if (dev_alloc(&oh, n) || dev_alloc(&ol, n)) rc = PAFUSE_E_CUDA;
     if (!rc) {

@@ -59,18 +59,32 @@ def _linear_case(M, N, K, epi, simt):
 
 @rung
 def linear_simt():
-    assert _linear_case(300, 224, 224, 0, True) < 1e-4
+    assert _linear_case(300, 224, 224, 0, True) < 2e-6
+
+
+def _cg(n):
+    _ctx().set_gemm_cta_group(n)
+
+
+@rung
+def linear_cg1_small():
+    _cg(1)
+    assert _linear_case(128, 256, 64, 0, False) < 2e-6
+    assert _linear_case(300, 224, 224, 0, False) < 2e-6
 
 
 @rung
 def linear_tc_small():
-    assert _linear_case(128, 256, 64, 0, False) < 1e-4
+    _cg(2)
+    assert _linear_case(128, 256, 64, 0, False) < 2e-6
 
 
 @rung
 def linear_tc_k():
-    assert _linear_case(128, 256, 256, 0, False) < 1e-4
-    assert _linear_case(256, 224, 224, 0, False) < 1e-4
+    _cg(2)
+    assert _linear_case(256, 256, 256, 0, False) < 2e-6
+    assert _linear_case(300, 224, 224, 0, False) < 2e-6
+    assert _linear_case(1000, 1152, 384, 0, False) < 2e-6
 
 
 @rung
@@ -78,13 +92,13 @@ def linear_tc_shapes():
     for (N, K) in [(1152, 384), (384, 384), (768, 384), (384, 768), (672, 224), (224, 224), (448, 224), (224, 448),
                    (768, 256), (256, 256), (512, 256), (256, 512)]:
         for epi in (0, 1, 2):
-            assert _linear_case(1000, N, K, epi, False) < 2e-4
+            assert _linear_case(1000, N, K, epi, False) < 3e-6
 
 
 @rung
 def linear_tc_big():
     import torch
-    assert _linear_case(148 * 128 * 3 + 77, 1152, 384, 0, False) < 2e-4
+    assert _linear_case(148 * 128 * 3 + 77, 1152, 384, 0, False) < 3e-6
     # throughput probe
     c = _ctx()
     from pafuse_b200 import _native
