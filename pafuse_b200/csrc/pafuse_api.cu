@@ -472,6 +472,7 @@ int pafuse_commit_weights(pafuse_ctx* ctx, void* stream) {
 int pafuse_pred_parts(pafuse_ctx* ctx, const float* x2d, const float* x3d, const float* sinus, float* out, int32_t B,
                       int32_t H, void* stream) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (B == 0) return 0;
     if (!x2d || !x3d || !sinus || !out || B < 0 || H < 1) {
         set_last_error("pafuse_pred_parts: bad argument");
         return PAFUSE_E_ARG;
@@ -485,6 +486,7 @@ int pafuse_ddim_step(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, c
                      int32_t last, double sqrt_recip, double sqrt_recipm1, double c64, float sqrt_an, float c,
                      float sigma, void* stream) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (B == 0) return 0;
     if (!x2d || !sinus || !img || !x0_out || B < 0 || H < 1 || (flip && !x2d_flip) || (!last && !noise)) {
         set_last_error("pafuse_ddim_step: bad argument");
         return PAFUSE_E_ARG;

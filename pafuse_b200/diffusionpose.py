@@ -218,6 +218,8 @@ class D3DP(nn.Module):
         x2d = inputs_2d.detach().to(torch.float32).contiguous()
         x2d_flip = input_2d_flip.detach().to(device=device, dtype=torch.float32).contiguous() if flip else None
         shape = (B, H, Fr, J, 3)
+        if B == 0:
+            return torch.empty((0, K, H, Fr, J, 3), dtype=torch.float32, device=device)
         with torch.cuda.device(device):
             img = self._draw(0, shape, device)                        # diffusionpose.py:283
             if self.noise_source is not None:
