@@ -17,7 +17,11 @@
 //   warp 0    TMA producer: 4 tiled loads per stage (A_hi, A_lo, W_hi, W_lo; 128B swizzle)
 //   warp 1    MMA issuer (even CTA only): 3 x (BK/16) tcgen05.mma per stage, commits to mbarriers
 //   warp 2    TMEM allocator (512 columns = two BN<=256 accumulator buffers)
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns, bias / GELU+split / residual, global stores
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns, bias / GELU+split, swizzled st.shared into a
+//             per-warp staging box, TMA store of the 32x32 box (cp.reduce.async.bulk .add for the
+//             residual update x += y, performed at the L2).  The first version stored straight from
+//             registers, one row per lane: 32 different 128-byte lines per store instruction made the
+//             epilogue, not the tensor pipe, the critical path (profiles/r1_gemm_1cta.txt).
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue),
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "kernels.cuh"
@@ -39,6 +43,8 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int TMEM_COLS = 512;
+constexpr int STG_WARP_BYTES = 8192;                // per epilogue warp: 2 staging buffers of 32 rows x 128 B
+constexpr int STG_BYTES = 4 * STG_WARP_BYTES;
 
 struct KernelParams {
     long long M;
@@ -49,15 +55,13 @@ struct KernelParams {
     int stage_bytes;                 // per CTA
     float out_scale;                 // undoes WEIGHT_SCALE
     const float* bias;
-    float* out_f32;
-    op_t* out_hi;
-    op_t* out_lo;
 };
 
 template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                  const __grid_constant__ CUtensorMap tm_out0, const __grid_constant__ CUtensorMap tm_out1,
                   const KernelParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -86,6 +90,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         prefetch_tensormap(&tm_a_lo);
         prefetch_tensormap(&tm_w_hi);
         prefetch_tensormap(&tm_w_lo);
+        prefetch_tensormap(&tm_out0);
+        if (EPI == EPI_GELU_SPLIT) prefetch_tensormap(&tm_out1);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -188,68 +194,89 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         int acc = 0;
         uint32_t acc_phase = 0;
         const float oscale = p.out_scale;
+        uint8_t* stg = smem + (size_t)p.stages * p.stage_bytes + q * STG_WARP_BYTES;   // 1024-byte aligned
+        int sbuf = 0;
         for (int tile = group; tile < num_tiles; tile += num_groups) {
             const int m_tile = tile / p.n_tiles;
             const int n_tile = tile % p.n_tiles;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
-            const long long row = (long long)(m_tile * CG + (int)cta_rank) * BM + q * 32 + lane;
-            const bool row_ok = row < p.M;
+            const int row0 = (m_tile * CG + (int)cta_rank) * BM + q * 32;   // first row of this warp's box
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32(t_base + (uint32_t)c0, r);
                 tmem_ld_wait();
-                const int col = n_tile * BN + c0;
-                if (row_ok) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-                    if (EPI == EPI_F32 || EPI == EPI_RESID) {
-                        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.N + col);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float4 bb = __ldg(b4 + i);
-                            float4 v;
-                            v.x = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bb.x);
-                            v.y = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bb.y);
-                            v.z = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bb.z);
-                            v.w = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bb.w);
-                            if (EPI == EPI_RESID) {
-                                float4 x = o4[i];
-                                v.x += x.x;
-                                v.y += x.y;
-                                v.z += x.z;
-                                v.w += x.w;
-                            }
-                            o4[i] = v;
-                        }
-                    } else {
-                        uint2* oh = reinterpret_cast<uint2*>(p.out_hi + (size_t)row * p.N + col);
-                        uint2* ol = reinterpret_cast<uint2*>(p.out_lo + (size_t)row * p.N + col);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float4 bb = __ldg(b4 + i);
-                            float v[4];
-                            v[0] = gelu_erf(fmaf(__uint_as_float(r[4 * i + 0]), oscale, bb.x));
-                            v[1] = gelu_erf(fmaf(__uint_as_float(r[4 * i + 1]), oscale, bb.y));
-                            v[2] = gelu_erf(fmaf(__uint_as_float(r[4 * i + 2]), oscale, bb.z));
-                            v[3] = gelu_erf(fmaf(__uint_as_float(r[4 * i + 3]), oscale, bb.w));
-                            uint2 hi, lo;
-                            split4(v, hi, lo);
-                            oh[i] = hi;
-                            ol[i] = lo;
-                        }
+                if (c0 + 32 >= BN) {                                  // accumulator fully read: hand the buffer back early
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {                                  // 4*CG arrivals release the buffer to the issuer
+                        if (CG == 1) mbar_arrive(&tmem_empty_bar[acc]);
+                        else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
                     }
                 }
-            }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {                                          // 4*CG arrivals release the buffer to the issuer
-                if (CG == 1) mbar_arrive(&tmem_empty_bar[acc]);
-                else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+                const int col = n_tile * BN + c0;
+                uint8_t* box = stg + sbuf * (STG_WARP_BYTES / 2);
+                if (lane == 0) bulk_wait_group_read<1>();             // the store that last used this buffer has read it
+                __syncwarp();
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+                if (EPI == EPI_F32 || EPI == EPI_RESID) {
+                    // 32 rows x 128 B, 128-byte swizzle: 16-byte chunk i of row r sits at chunk i ^ (r & 7)
+                    uint8_t* rowp = box + lane * 128;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 bb = __ldg(b4 + i);
+                        float4 v;
+                        v.x = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bb.x);
+                        v.y = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bb.y);
+                        v.z = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bb.z);
+                        v.w = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bb.w);
+                        *reinterpret_cast<float4*>(rowp + ((i ^ (lane & 7)) << 4)) = v;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (EPI == EPI_RESID) tma_reduce_add_2d(&tm_out0, box, col, row0);
+                        else tma_store_2d(&tm_out0, box, col, row0);
+                        bulk_commit_group();
+                    }
+                } else {
+                    // two boxes of 32 rows x 64 B (hi, lo), 64-byte swizzle: chunk i of row r at i ^ ((r >> 1) & 3)
+                    uint8_t* rowh = box + lane * 64;
+                    uint8_t* rowl = rowh + 2048;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 b0 = __ldg(b4 + 2 * i), b1 = __ldg(b4 + 2 * i + 1);
+                        float v[8];
+                        v[0] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 0]), oscale, b0.x));
+                        v[1] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 1]), oscale, b0.y));
+                        v[2] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 2]), oscale, b0.z));
+                        v[3] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 3]), oscale, b0.w));
+                        v[4] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 4]), oscale, b1.x));
+                        v[5] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 5]), oscale, b1.y));
+                        v[6] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 6]), oscale, b1.z));
+                        v[7] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 7]), oscale, b1.w));
+                        uint2 h0, l0, h1, l1;
+                        split4(v, h0, l0);
+                        split4(v + 4, h1, l1);
+                        const int off = (i ^ ((lane >> 1) & 3)) << 4;
+                        *reinterpret_cast<uint4*>(rowh + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                        *reinterpret_cast<uint4*>(rowl + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tm_out0, box, col, row0);
+                        tma_store_2d(&tm_out1, box + 2048, col, row0);
+                        bulk_commit_group();
+                    }
+                }
+                sbuf ^= 1;
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (lane == 0) bulk_wait_group<0>();                          // all output boxes are written before the CTA retires
     }
 
     tcgen05_fence_before();
@@ -279,12 +306,30 @@ int make_map_f16(CUtensorMap* map, const void* ptr, long long rows, int K, int b
     return 0;
 }
 
+// output boxes of the epilogue: 32 columns x 32 rows, swizzle = the 128 (fp32) / 64 (fp16) bytes of one box row
+int make_map_out(CUtensorMap* map, const void* ptr, long long rows, int N, bool f32) {
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)N * (f32 ? 4 : 2)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                          const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(out) failed (%d) rows=%lld N=%d ptr=%p", (int)r, rows, N, ptr);
+        return -2;
+    }
+    return 0;
+}
+
 int g_num_sms = 0;
 int g_force_cg = 0;      // PAFUSE_GEMM_CTA_GROUP=1|2 overrides the default (2)
 
 template <int EPI, int CG>
 int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
-               const KernelParams& kp, int grid, int smem, cudaStream_t st) {
+               const CUtensorMap& o0, const CUtensorMap& o1, const KernelParams& kp, int grid, int smem,
+               cudaStream_t st) {
     auto kern = gemm_f16x3_kernel<EPI, CG>;
     static bool configured = false;                                   // per template instance
     if (!configured) {
@@ -303,7 +348,7 @@ int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PAFUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ah, al, wh, wl, kp));
+    PAFUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ah, al, wh, wl, o0, o1, kp));
     PAFUSE_LAUNCH_OK();
     return 0;
 }
@@ -329,22 +374,27 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     kp.m_tiles = (int)((g.M + BM * CG - 1) / (BM * CG));
     kp.n_tiles = g.N / BN;
     kp.stage_bytes = 2 * A_TILE_BYTES + 2 * (BN / CG) * BK * 2;
-    int stages = (SMEM_LIMIT - 2048 - 1024) / kp.stage_bytes;         // 1 KiB alignment slack + static barriers
+    int stages = (SMEM_LIMIT - 2048 - 1024 - STG_BYTES) / kp.stage_bytes;   // 1 KiB alignment slack + static barriers
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     kp.stages = stages;
     kp.out_scale = g.out_scale;
     kp.bias = g.bias;
-    kp.out_f32 = g.out_f32;
-    kp.out_hi = g.out_hi;
-    kp.out_lo = g.out_lo;
-    const int smem = stages * kp.stage_bytes + 1024;
+    CUtensorMap o0, o1;
+    if (g.epilogue == EPI_GELU_SPLIT) {
+        if (int rc = make_map_out(&o0, g.out_hi, g.M, g.N, false)) return rc;
+        if (int rc = make_map_out(&o1, g.out_lo, g.M, g.N, false)) return rc;
+    } else {
+        if (int rc = make_map_out(&o0, g.out_f32, g.M, g.N, true)) return rc;
+        o1 = o0;
+    }
+    const int smem = stages * kp.stage_bytes + STG_BYTES + 1024;
     const long long tiles = (long long)kp.m_tiles * kp.n_tiles;
     const int max_groups = g_num_sms / CG;
     const int grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;
     switch (g.epilogue) {
-        case EPI_F32: return launch_epi<EPI_F32, CG>(ah, al, wh, wl, kp, grid, smem, st);
-        case EPI_GELU_SPLIT: return launch_epi<EPI_GELU_SPLIT, CG>(ah, al, wh, wl, kp, grid, smem, st);
-        case EPI_RESID: return launch_epi<EPI_RESID, CG>(ah, al, wh, wl, kp, grid, smem, st);
+        case EPI_F32: return launch_epi<EPI_F32, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
+        case EPI_GELU_SPLIT: return launch_epi<EPI_GELU_SPLIT, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
+        case EPI_RESID: return launch_epi<EPI_RESID, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
     }
     set_last_error("gemm: bad epilogue %d", g.epilogue);
     return -1;
