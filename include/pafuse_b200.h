@@ -137,6 +137,8 @@ int pafuse_attention(pafuse_ctx* ctx, const float* qkv, float* out, int32_t S, i
 
 /* debugging switch: route the path's GEMMs through the CUDA-core reference kernel */
 int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable);
+/* debugging switch: CUDA-core attention kernel instead of the tcgen05 one */
+int pafuse_set_debug_simt_attention(pafuse_ctx* ctx, int32_t enable);
 /* process-wide: 2 (default) = tcgen05 CTA pairs (cta_group::2, 256-row tiles), 1 = lone CTAs */
 int pafuse_set_gemm_cta_group(int32_t cta_group);
 

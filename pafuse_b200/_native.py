@@ -50,6 +50,7 @@ _SIGNATURES = {
     "pafuse_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "pafuse_set_debug_simt_gemm": (c_int32, [c_void_p, c_int32]),
     "pafuse_set_gemm_cta_group": (c_int32, [c_int32]),
+    "pafuse_set_debug_simt_attention": (c_int32, [c_void_p, c_int32]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -254,6 +255,9 @@ class NativeContext:
         with torch.cuda.device(self.device):
             check(self.lib.pafuse_profile_read(self.handle, ms, work, cnt, n), "pafuse_profile_read")
         return {name: (ms[i], work[i], int(cnt[i])) for i, name in enumerate(self.PROFILE_CATEGORIES)}
+
+    def set_debug_simt_attention(self, enable: bool):
+        check(self.lib.pafuse_set_debug_simt_attention(self.handle, 1 if enable else 0), "pafuse_set_debug_simt_attention")
 
     def set_gemm_cta_group(self, cta_group: int):
         with torch.cuda.device(self.device):

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpafuse_b200.so")
-SOURCES = ["pafuse_api.cu", "gemm_tcgen05.cu", "attention.cu", "elementwise.cu"]
+SOURCES = ["pafuse_api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "elementwise.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "pafuse_b200.h")]
 
 

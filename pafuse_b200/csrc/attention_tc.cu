@@ -1,0 +1,495 @@
+// Short-sequence attention of the STE / TTE blocks (mixste.py:63-82, comb=False) on the
+// sm_100a tensor cores.
+//
+// The sequences are tiny (24 / 68 / 42 joints, 27 frames) while tcgen05.mma wants M = 128, so a
+// tile packs G whole sequences ("groups") of L rows: body 5x24, face 1x68, hands 3x42 joints of
+// consecutive tokens; 4 joints x 27 frames of one clip-hypothesis for the temporal blocks.  Per
+// (tile, head) the kernel computes the full 128 x 128 score matrix S = Q K^T with three f16x3
+// passes into TMEM, applies a block-diagonal mask (a query only sees the keys of its own
+// group) inside the softmax, writes the un-normalised probabilities back to TMEM as fp16 hi/lo
+// (the A operand of the second MMA is read from tensor memory), and computes O = P V with V as
+// an MN-major shared-memory operand.  The off-diagonal work is wasted tensor math, which is
+// cheap; the CUDA-core version of this kernel spent 28 % of the whole step on 3.3 % of the FLOPs.
+//
+// Inputs are the per-head planes the qkv GEMM epilogue writes: fp16 hi/lo arrays
+// [which(q,k,v) * 8 + head][token][hdp] with the head dimension zero-padded to hdp = 64 / 32
+// so that one tile row is exactly one 128- or 64-byte swizzle span.
+//
+//   warp 0     TMA producer: Q,K,V hi/lo tiles of one (tile, head) per stage (2 stages)
+//   warp 1     MMA issuer:   S = QK^T (double-buffered in TMEM), O = PV
+//   warp 2     TMEM allocator
+//   warps 4-7  softmax: thread = tile row = TMEM lane; row max / exp2 / sum without shuffles,
+//              P -> TMEM, O -> registers -> 1/sum -> fp16 hi/lo -> global [token, C]
+#include "kernels.cuh"
+
+#include <cudaTypedefs.h>
+#include <math.h>
+
+namespace pafuse {
+
+namespace {
+
+constexpr int TILE_ROWS = 128;
+constexpr int NSTAGE = 2;
+constexpr int ATT_THREADS = 256;
+// TMEM columns
+constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_PHI = 256, TM_PLO = 320, TM_O0 = 384, TM_O1 = 448;
+
+struct AttnTcParams {
+    int num_tiles;
+    int L, G;                 // group length and groups per tile (G*L <= 128)
+    int hd, hdp, C;
+    int temporal;
+    int J, F;
+    int tiles_per_seq;        // temporal: ceil(J / 4)
+    long long M;              // valid token rows
+    float scale_log2e;        // hd^-0.5 * log2(e)
+    op_t* o_hi;
+    op_t* o_lo;
+};
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(sbo_bytes >> 4) << 16;           // leading byte offset (not used by these shapes)
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;           // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)layout << 61;                     // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+    return d;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t r[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                    const AttnTcParams p) {
+    constexpr int ROWB = HDP * 2;                              // bytes per tile row = swizzle span
+    constexpr int TILE_BYTES = TILE_ROWS * ROWB;
+    constexpr int STAGE_BYTES = 6 * TILE_BYTES;                // Qh Ql Kh Kl Vh Vl
+    constexpr uint32_t LAYOUT = HDP == 64 ? 2u : 4u;
+    constexpr uint32_t SBO = 8 * ROWB;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE];
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2], o_full[2], o_empty[2], p_full, p_empty;
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_units = p.num_tiles * 8;
+    const int rows_used = p.G * p.L;                           // tile rows that hold tokens
+    const int load_rows = p.temporal ? rows_used : TILE_ROWS;  // rows each TMA box writes
+    const int key_steps = (rows_used + 15) / 16;               // 16-key MMA steps that can hold live keys
+
+    // rows a temporal box never writes must not hold NaN bit patterns (0 * NaN in the PV product)
+    for (int i = threadIdx.x; i < NSTAGE * STAGE_BYTES / 16; i += ATT_THREADS)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tm_hi);
+        prefetch_tensormap(&tm_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], 4);
+            mbar_init(&o_full[s], 1);
+            mbar_init(&o_empty[s], 4);
+        }
+        mbar_init(&p_full, 4);
+        mbar_init(&p_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(&tmem_base_slot, 512);
+        tmem_relinquish<1>();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+                const int stage = it & 1;
+                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                const int tile = u >> 3, head = u & 7;
+                mbar_wait(&empty_bar[stage], ph ^ 1);
+                uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(6 * load_rows * ROWB));
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {                  // q, k, v
+                    const int plane = w * 8 + head;
+                    if (!p.temporal) {
+                        const int row0 = tile * rows_used;
+                        tma_load_3d(st + (2 * w) * TILE_BYTES, &tm_hi, &full_bar[stage], 0, row0, plane);
+                        tma_load_3d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, &full_bar[stage], 0, row0, plane);
+                    } else {
+                        const int s = tile / p.tiles_per_seq;
+                        const int j0 = (tile % p.tiles_per_seq) * p.G;
+                        tma_load_4d(st + (2 * w) * TILE_BYTES, &tm_hi, &full_bar[stage], 0, s * p.F, j0, plane);
+                        tma_load_4d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, &full_bar[stage], 0, s * p.F, j0, plane);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc_qk = make_idesc_f16(128, 128);
+            const uint32_t idesc_pv = make_idesc_f16(128, HDP) | (1u << 16);      // B (= V) is MN-major
+            const int n_local = (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            auto issue_qk = [&](int it) {
+                const int stage = it & 1;
+                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&full_bar[stage], ph);
+                mbar_wait(&s_empty[stage], ph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                const uint32_t d = tmem_base + (stage ? TM_S1 : TM_S0);
+#pragma unroll
+                for (int k = 0; k < HDP / 16; ++k) {
+                    const uint32_t ko = (uint32_t)k * 32u;
+                    const uint64_t qh = make_desc(sa + ko, SBO, LAYOUT), ql = make_desc(sa + TILE_BYTES + ko, SBO, LAYOUT);
+                    const uint64_t kh = make_desc(sa + 2 * TILE_BYTES + ko, SBO, LAYOUT);
+                    const uint64_t kl = make_desc(sa + 3 * TILE_BYTES + ko, SBO, LAYOUT);
+                    umma_f16_ss<1>(d, ql, kh, idesc_qk, k != 0 ? 1u : 0u);
+                    umma_f16_ss<1>(d, qh, kl, idesc_qk, 1u);
+                    umma_f16_ss<1>(d, qh, kh, idesc_qk, 1u);
+                }
+                umma_commit<1>(&s_full[stage]);
+            };
+            if (n_local > 0) issue_qk(0);
+            for (int it = 0; it < n_local; ++it) {
+                if (it + 1 < n_local) issue_qk(it + 1);
+                const int stage = it & 1;
+                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&p_full, (uint32_t)it & 1u);
+                mbar_wait(&o_empty[stage], ph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                const uint32_t d = tmem_base + (stage ? TM_O1 : TM_O0);
+                for (int k = 0; k < key_steps; ++k) {
+                    const uint32_t vo = (uint32_t)k * 16u * ROWB;                 // 16 keys further down the V tile
+                    const uint64_t vh = make_desc(sa + 4 * TILE_BYTES + vo, SBO, LAYOUT);
+                    const uint64_t vl = make_desc(sa + 5 * TILE_BYTES + vo, SBO, LAYOUT);
+                    const uint32_t ph_a = tmem_base + TM_PHI + (uint32_t)k * 8u;  // 16 fp16 keys = 8 columns
+                    const uint32_t pl_a = tmem_base + TM_PLO + (uint32_t)k * 8u;
+                    umma_f16_ts(d, pl_a, vh, idesc_pv, k != 0 ? 1u : 0u);
+                    umma_f16_ts(d, ph_a, vl, idesc_pv, 1u);
+                    umma_f16_ts(d, ph_a, vh, idesc_pv, 1u);
+                }
+                umma_commit<1>(&empty_bar[stage]);
+                umma_commit<1>(&p_empty);
+                umma_commit<1>(&o_full[stage]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== softmax + output =====================
+        const int q = warp - 4;
+        const int r = q * 32 + lane;                           // tile row == TMEM lane
+        const bool row_live = r < rows_used;
+        const int g = row_live ? r / p.L : 0;
+        const int klo = g * p.L, khi = klo + p.L;              // this row's keys
+        // keys any row of this warp can see (warp-uniform)
+        const int w_first = q * 32, w_last = min(q * 32 + 31, rows_used - 1);
+        const int wlo = w_first < rows_used ? (w_first / p.L) * p.L : 0;
+        const int whi = w_first < rows_used ? (w_last / p.L + 1) * p.L : 0;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        int it = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+            const int stage = it & 1;
+            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            const int tile = u >> 3, head = u & 7;
+            const uint32_t s_addr = tmem_base + lane_sel + (stage ? TM_S1 : TM_S0);
+            mbar_wait(&s_full[stage], ph);
+            tcgen05_fence_after();
+            // ---- pass 1: row maximum over the row's own keys
+            float mx = -INFINITY;
+            for (int c0 = 0; c0 < key_steps * 16; c0 += 32) {
+                if (c0 + 32 <= wlo || c0 >= whi) continue;     // warp-uniform: no live key of this warp in the chunk
+                uint32_t sv[32];
+                tmem_ld_32x32(s_addr + (uint32_t)c0, sv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int c = c0 + i;
+                    if (c >= klo && c < khi) mx = fmaxf(mx, __uint_as_float(sv[i]));
+                }
+            }
+            if (!row_live) mx = 0.f;
+            const float moff = mx * p.scale_log2e;
+            // ---- pass 2: p = exp2(s*c - m*c), row sum, fp16 hi/lo into TMEM (zeros outside the group)
+            mbar_wait(&p_empty, ((uint32_t)it & 1u) ^ 1u);     // PV of the previous unit has consumed P
+            tcgen05_fence_after();
+            float sum = 0.f;
+            for (int c0 = 0; c0 < key_steps * 16; c0 += 32) {
+                uint32_t hi16[16], lo16[16];
+                if (c0 + 32 <= wlo || c0 >= whi) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) hi16[i] = lo16[i] = 0u;
+                } else {
+                    uint32_t sv[32];
+                    tmem_ld_32x32(s_addr + (uint32_t)c0, sv);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float pv[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int c = c0 + 2 * i + e;
+                            float v = 0.f;
+                            if (row_live && c >= klo && c < khi)
+                                v = fast_exp2(fmaf(__uint_as_float(sv[2 * i + e]), p.scale_log2e, -moff));
+                            pv[e] = v;
+                            sum += v;
+                        }
+                        op_t h0, l0, h1, l1;
+                        split_op(pv[0], h0, l0);
+                        split_op(pv[1], h1, l1);
+                        hi16[i] = pack_op2(h0, h1);
+                        lo16[i] = pack_op2(l0, l1);
+                    }
+                }
+                tmem_st_32x16(tmem_base + lane_sel + TM_PHI + (uint32_t)(c0 >> 1), hi16);
+                tmem_st_32x16(tmem_base + lane_sel + TM_PLO + (uint32_t)(c0 >> 1), lo16);
+            }
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&p_full);                          // P is in tensor memory
+                mbar_arrive(&s_empty[stage]);                  // S has been read twice, QK of unit it+2 may overwrite it
+            }
+            // ---- output: O / sum -> fp16 hi/lo -> global
+            mbar_wait(&o_full[stage], ph);
+            tcgen05_fence_after();
+            uint32_t ov[HDP];
+            const uint32_t o_addr = tmem_base + lane_sel + (stage ? TM_O1 : TM_O0);
+            tmem_ld_32x32(o_addr, ov);
+            if (HDP == 64) tmem_ld_32x32(o_addr + 32u, ov + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[stage]);
+            long long token = -1;
+            if (row_live) {
+                if (!p.temporal) {
+                    token = (long long)tile * rows_used + r;
+                } else {
+                    const int s = tile / p.tiles_per_seq;
+                    const int j = (tile % p.tiles_per_seq) * p.G + g;
+                    const int f = r - g * p.L;
+                    token = j < p.J ? ((long long)s * p.F + f) * p.J + j : -1;
+                }
+                if (token >= p.M) token = -1;
+            }
+            if (token >= 0) {
+                const float inv = 1.0f / sum;
+                uint2* oh = reinterpret_cast<uint2*>(p.o_hi + (size_t)token * p.C + head * p.hd);
+                uint2* ol = reinterpret_cast<uint2*>(p.o_lo + (size_t)token * p.C + head * p.hd);
+#pragma unroll
+                for (int i = 0; i < HDP / 4; ++i) {
+                    if (4 * i < p.hd) {
+                        float v4[4] = {__uint_as_float(ov[4 * i + 0]) * inv, __uint_as_float(ov[4 * i + 1]) * inv,
+                                       __uint_as_float(ov[4 * i + 2]) * inv, __uint_as_float(ov[4 * i + 3]) * inv};
+                        uint2 h, l;
+                        split4(v4, h, l);
+                        oh[i] = h;
+                        ol[i] = l;
+                    }
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<1>(tmem_base, 512);
+    }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
+int g_sms = 0;
+
+int att_init() {
+    if (g_enc) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PAFUSE_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+        set_last_error("cuTensorMapEncodeTiled not available from the driver");
+        return -2;
+    }
+    g_enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    int dev = 0;
+    PAFUSE_CUDA_OK(cudaGetDevice(&dev));
+    PAFUSE_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    return 0;
+}
+
+// planes [24][rows_cap][hdp] fp16.  Spatial: (hdp, rows_cap, 24), box (hdp, 128, 1).
+// Temporal: (hdp, S*F [stride J*hdp], J [stride hdp], 24), box (hdp, F, G, 1): the box lands in shared
+// memory joint-major, i.e. as G groups of F consecutive rows.
+int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int hdp, bool temporal, int J, int F, int G) {
+    const CUtensorMapSwizzle sw = hdp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r;
+    if (!temporal) {
+        cuuint64_t dims[3] = {(cuuint64_t)hdp, (cuuint64_t)rows_cap, 24};
+        cuuint64_t strides[2] = {(cuuint64_t)hdp * 2, (cuuint64_t)rows_cap * hdp * 2};
+        cuuint32_t box[3] = {(cuuint32_t)hdp, TILE_ROWS, 1};
+        r = g_enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<op_t*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[4] = {(cuuint64_t)hdp, (cuuint64_t)(rows_cap / J), (cuuint64_t)J, 24};
+        cuuint64_t strides[3] = {(cuuint64_t)J * hdp * 2, (cuuint64_t)hdp * 2, (cuuint64_t)rows_cap * hdp * 2};
+        cuuint32_t box[4] = {(cuuint32_t)hdp, (cuuint32_t)F, (cuuint32_t)G, 1};
+        r = g_enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<op_t*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(attention planes) failed (%d) rows_cap=%lld hdp=%d temporal=%d", (int)r,
+                       rows_cap, hdp, (int)temporal);
+        return -2;
+    }
+    return 0;
+}
+
+template <int HDP>
+int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, cudaStream_t st) {
+    constexpr int SMEM = NSTAGE * 6 * TILE_ROWS * HDP * 2 + 1024;
+    auto kern = attention_tc_kernel<HDP>;
+    static bool configured = false;
+    if (!configured) {
+        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    const long long units = (long long)p.num_tiles * 8;
+    const int grid = (int)(units < g_sms ? units : g_sms);
+    kern<<<grid, ATT_THREADS, SMEM, st>>>(mh, ml, p);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace
+
+int attn_head_pad(int hd) { return hd > 32 ? 64 : 32; }
+
+// groups per 128-row tile
+static int groups_per_tile(int L, bool temporal) { return temporal ? 4 : 128 / L; }
+
+int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int F, int J, int C, int temporal,
+                        cudaStream_t st) {
+    if (S == 0) return 0;
+    if (int rc = att_init()) return rc;
+    const int hd = C / 8, hdp = attn_head_pad(hd);
+    if (hd > 64 || hd % 4 != 0 || (temporal ? F : J) > 128 || pl.hdp != hdp || (temporal && pl.rows_cap % J != 0)) {
+        set_last_error("attention_tc: unsupported shape J=%d F=%d C=%d temporal=%d", J, F, C, temporal);
+        return -1;
+    }
+    AttnTcParams p;
+    p.temporal = temporal ? 1 : 0;
+    p.L = temporal ? F : J;
+    p.G = groups_per_tile(p.L, temporal != 0);
+    p.hd = hd;
+    p.hdp = hdp;
+    p.C = C;
+    p.J = J;
+    p.F = F;
+    p.M = (long long)S * F * J;
+    if (temporal) {
+        p.tiles_per_seq = (J + p.G - 1) / p.G;
+        p.num_tiles = S * p.tiles_per_seq;
+    } else {
+        p.tiles_per_seq = 0;
+        const long long rows_per_tile = (long long)p.G * p.L;
+        p.num_tiles = (int)((p.M + rows_per_tile - 1) / rows_per_tile);
+    }
+    p.scale_log2e = (float)(pow((double)hd, -0.5) * 1.4426950408889634);
+    p.o_hi = o_hi;
+    p.o_lo = o_lo;
+    CUtensorMap mh, ml;
+    if (int rc = make_plane_map(&mh, pl.hi, pl.rows_cap, hdp, temporal != 0, J, F, p.G)) return rc;
+    if (int rc = make_plane_map(&ml, pl.lo, pl.rows_cap, hdp, temporal != 0, J, F, p.G)) return rc;
+    return hdp == 64 ? launch_tc<64>(mh, ml, p, st) : launch_tc<32>(mh, ml, p, st);
+}
+
+// fp32 qkv [M,3C] -> head planes (unit tests; the production path gets the planes from the qkv GEMM epilogue)
+__global__ void qkv_to_planes_kernel(const float* __restrict__ qkv, op_t* __restrict__ hi, op_t* __restrict__ lo,
+                                     long long M, long long rows_cap, int C, int hd, int hdp) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = M * 24 * hdp;
+    if (idx >= total) return;
+    const int d = (int)(idx % hdp);
+    long long t = idx / hdp;
+    const long long m = t % M;
+    const int plane = (int)(t / M);
+    float v = 0.f;
+    if (d < hd) v = qkv[(size_t)m * 3 * C + (plane / 8) * C + (plane % 8) * hd + d];
+    op_t h, l;
+    split_op(v, h, l);
+    const size_t o = ((size_t)plane * rows_cap + m) * hdp + d;
+    hi[o] = h;
+    lo[o] = l;
+}
+
+int launch_qkv_to_planes(const float* qkv, const AttnPlanes& pl, long long M, int C, cudaStream_t st) {
+    const int hd = C / 8;
+    const long long total = M * 24 * pl.hdp;
+    if (total == 0) return 0;
+    qkv_to_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(qkv, pl.hi, pl.lo, M, pl.rows_cap, C, hd, pl.hdp);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace pafuse

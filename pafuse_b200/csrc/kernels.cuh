@@ -86,6 +86,14 @@ struct AttnParams {
     float scale;              // head_dim^-0.5, set by launch_attention
 };
 
+// q/k/v of one part as per-head planes [which*8 + head][rows_cap][hdp], fp16 hi/lo (attention_tc.cu)
+struct AttnPlanes {
+    op_t* hi;
+    op_t* lo;
+    long long rows_cap;       // rows per plane (multiple of J)
+    int hdp;                  // head dim padded to 64 / 32
+};
+
 enum GemmEpilogue { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_RESID = 2 };
 
 struct GemmArgs {
@@ -113,7 +121,11 @@ int launch_negate_rows(float* x, const int* rows, int nrows, long long poses, in
 int launch_project(const float* X, const float* cam, float* out, long long npts, long long pts_per_cam,
                    cudaStream_t st);
 int launch_aggregate(const AggParams& p, cudaStream_t st);
-int launch_attention(const AttnParams& p, cudaStream_t st);
+int launch_attention(const AttnParams& p, cudaStream_t st);          // CUDA-core version (debug reference)
+int attn_head_pad(int hd);
+int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int F, int J, int C, int temporal,
+                        cudaStream_t st);
+int launch_qkv_to_planes(const float* qkv, const AttnPlanes& pl, long long M, int C, cudaStream_t st);
 
 // tcgen05 GEMM (f16x3 split precision).  Tensor maps are built per call from the raw pointers.
 int gemm_init();                                            // resolves cuTensorMapEncodeTiled

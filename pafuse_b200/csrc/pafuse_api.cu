@@ -48,9 +48,11 @@ struct Part {
 
 struct Workspace {
     long long rows_x_c = 0;   // capacity in (rows * C) units
+    size_t plane_halves = 0;
     float* x = nullptr;
     op_t *a_hi = nullptr, *a_lo = nullptr;
     float* qkv = nullptr;
+    op_t *pl_hi = nullptr, *pl_lo = nullptr;   // q/k/v head planes, 24 * rows * 64 halves each
     op_t *o_hi = nullptr, *o_lo = nullptr;
     op_t *h_hi = nullptr, *h_lo = nullptr;
 };
@@ -98,6 +100,7 @@ struct pafuse_ctx {
     size_t pred_cap = 0;             // floats
     bool committed = false;
     bool debug_simt = false;
+    bool debug_simt_attn = false;
     Profiler prof;
 };
 
@@ -182,13 +185,18 @@ int dev_alloc(T** p, size_t n) {
 int ensure_workspace(pafuse_ctx* ctx, long long rows_x_c) {
     Workspace& w = ctx->ws;
     if (rows_x_c <= w.rows_x_c) return 0;
-    cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv);
+    cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv); cudaFree(w.pl_hi); cudaFree(w.pl_lo);
     cudaFree(w.o_hi); cudaFree(w.o_lo); cudaFree(w.h_hi); cudaFree(w.h_lo);
     w = Workspace();
     size_t n = (size_t)rows_x_c;
     if (dev_alloc(&w.x, n)) return PAFUSE_E_CUDA;
     if (dev_alloc(&w.a_hi, n) || dev_alloc(&w.a_lo, n)) return PAFUSE_E_CUDA;
     if (dev_alloc(&w.qkv, 3 * n)) return PAFUSE_E_CUDA;
+    // planes: rows * 24 * hdp halves with rows*C = n and hdp <= 64 = 8*hdp/C * ... -> 24*64/(8*28) * n upper bound
+    w.plane_halves = (size_t)((double)n * 24.0 * 64.0 / 224.0) + 4096;
+    if (dev_alloc(&w.pl_hi, w.plane_halves) || dev_alloc(&w.pl_lo, w.plane_halves)) return PAFUSE_E_CUDA;
+    PAFUSE_CUDA_OK(cudaMemset(w.pl_hi, 0, w.plane_halves * sizeof(op_t)));
+    PAFUSE_CUDA_OK(cudaMemset(w.pl_lo, 0, w.plane_halves * sizeof(op_t)));
     if (dev_alloc(&w.o_hi, n) || dev_alloc(&w.o_lo, n)) return PAFUSE_E_CUDA;
     if (dev_alloc(&w.h_hi, 2 * n) || dev_alloc(&w.h_lo, 2 * n)) return PAFUSE_E_CUDA;
     w.rows_x_c = rows_x_c;
@@ -297,7 +305,18 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
                 {
                     const double L = temporal ? (double)F : (double)J;
                     ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st);
-                    if (int rc = launch_attention(a, st)) return rc;
+                    if (ctx->debug_simt_attn) {
+                        if (int rc = launch_attention(a, st)) return rc;
+                    } else {
+                        AttnPlanes pl;
+                        pl.hi = w.pl_hi; pl.lo = w.pl_lo; pl.rows_cap = M; pl.hdp = attn_head_pad(C / 8);
+                        if ((size_t)24 * M * pl.hdp > w.plane_halves) {
+                            set_last_error("attention plane workspace too small");
+                            return PAFUSE_E_STATE;
+                        }
+                        if (int rc = launch_qkv_to_planes(w.qkv, pl, M, C, st)) return rc;
+                        if (int rc = launch_attention_tc(pl, w.o_hi, w.o_lo, Sc, F, J, C, temporal ? 1 : 0, st)) return rc;
+                    }
                 }
 
                 g.a_hi = w.o_hi; g.a_lo = w.o_lo;
@@ -419,7 +438,7 @@ void pafuse_destroy(pafuse_ctx* ctx) {
         cudaFree(p.f32); cudaFree(p.hi); cudaFree(p.lo); cudaFree(p.joints_dev); cudaFree(p.temb);
     }
     Workspace& w = ctx->ws;
-    cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv);
+    cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv); cudaFree(w.pl_hi); cudaFree(w.pl_lo);
     cudaFree(w.o_hi); cudaFree(w.o_lo); cudaFree(w.h_hi); cudaFree(w.h_lo);
     cudaFree(ctx->flip_perm_dev); cudaFree(ctx->conn_dev); cudaFree(ctx->conn_rows_dev); cudaFree(ctx->pred);
     delete ctx;
@@ -576,6 +595,12 @@ int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable) {
     return 0;
 }
 
+int pafuse_set_debug_simt_attention(pafuse_ctx* ctx, int32_t enable) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    ctx->debug_simt_attn = enable != 0;
+    return 0;
+}
+
 int pafuse_set_gemm_cta_group(int32_t cta_group) {
     if (cta_group != 1 && cta_group != 2) {
         set_last_error("pafuse_set_gemm_cta_group: cta_group must be 1 or 2");
@@ -671,19 +696,31 @@ int pafuse_attention(pafuse_ctx* ctx, const float* qkv, float* out, int32_t S, i
         return PAFUSE_E_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    size_t n = (size_t)S * ctx->cfg.frames * J * C;
-    op_t *oh = nullptr, *ol = nullptr;
+    const long long M = (long long)S * ctx->cfg.frames * J;
+    size_t n = (size_t)M * C;
+    op_t *oh = nullptr, *ol = nullptr, *ph = nullptr, *pl = nullptr;
     int rc = 0;
     if (dev_alloc(&oh, n) || dev_alloc(&ol, n)) rc = PAFUSE_E_CUDA;
     if (!rc) {
-        AttnParams a;
-        a.qkv = qkv; a.out_hi = oh; a.out_lo = ol; a.S = S; a.F = ctx->cfg.frames; a.J = J; a.C = C;
-        a.temporal = temporal; a.scale = 0.f;
-        rc = launch_attention(a, st);
+        if (ctx->debug_simt_attn) {
+            AttnParams a;
+            a.qkv = qkv; a.out_hi = oh; a.out_lo = ol; a.S = S; a.F = ctx->cfg.frames; a.J = J; a.C = C;
+            a.temporal = temporal; a.scale = 0.f;
+            rc = launch_attention(a, st);
+        } else {
+            AttnPlanes planes;
+            planes.hdp = attn_head_pad(C / 8);
+            planes.rows_cap = M;
+            size_t halves = (size_t)24 * M * planes.hdp;
+            if (dev_alloc(&ph, halves) || dev_alloc(&pl, halves)) rc = PAFUSE_E_CUDA;
+            planes.hi = ph; planes.lo = pl;
+            if (!rc) rc = launch_qkv_to_planes(qkv, planes, M, C, st);
+            if (!rc) rc = launch_attention_tc(planes, oh, ol, S, ctx->cfg.frames, J, C, temporal, st);
+        }
         if (!rc) join_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(oh, ol, out, n);
     }
     cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(oh); cudaFree(ol);
+    cudaFree(oh); cudaFree(ol); cudaFree(ph); cudaFree(pl);
     if (!rc && e != cudaSuccess) {
         set_last_error("pafuse_attention: %s", cudaGetErrorString(e));
         rc = PAFUSE_E_CUDA;

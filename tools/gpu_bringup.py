@@ -117,14 +117,14 @@ def linear_tc_big():
           f"algorithmic {2 * M * N * K / 1e12:.2f} TFLOP")
 
 
-@rung
-def attention():
+def _attention(simt, cases, S=3):
     import torch
     torch.manual_seed(0)
     c = _ctx()
-    for (J, C) in [(24, 384), (68, 224), (42, 256)]:
+    c.set_debug_simt_attention(simt)
+    for (J, C) in cases:
         for temporal in (False, True):
-            S, F = 3, 27
+            F = 27
             qkv = torch.randn(S * F * J, 3 * C, device="cuda")
             out = c.attention(qkv, S, J, C, temporal)
             torch.cuda.synchronize()
@@ -139,8 +139,33 @@ def attention():
             a = a.permute(0, 3, 1, 2, 4) if temporal else a.permute(0, 1, 3, 2, 4)   # -> (S,F,J,8,hd)
             ref = a.reshape(S * F * J, C)
             err = (out.double() - ref).abs().max().item()
-            print(f"attention J={J} C={C} temporal={temporal}: max abs err {err:.3e}")
-            assert err < 1e-4
+            print(f"attention simt={simt} S={S} J={J} C={C} temporal={temporal}: max abs err {err:.3e}", flush=True)
+            assert err < 2e-5
+
+
+@rung
+def attention():
+    _attention(True, [(24, 384), (68, 224), (42, 256)])
+
+
+@rung
+def attention_tc_hands():
+    _attention(False, [(42, 256)])
+
+
+@rung
+def attention_tc_face():
+    _attention(False, [(68, 224)])
+
+
+@rung
+def attention_tc_body():
+    _attention(False, [(24, 384)])
+
+
+@rung
+def attention_tc_big():
+    _attention(False, [(24, 384), (68, 224), (42, 256)], S=37)
 
 
 @rung
