@@ -135,6 +135,12 @@ int pafuse_linear(pafuse_ctx* ctx, const float* x, const float* w, const float* 
 int pafuse_attention(pafuse_ctx* ctx, const float* qkv, float* out, int32_t S, int32_t J, int32_t C, int32_t temporal,
                      void* stream);
 
+/* Attention.forward up to (excluding) proj (mixste.py:63-79) the way the path runs it: the qkv GEMM
+ * writes fp16 hi/lo head planes from its epilogue, the tcgen05 attention kernel consumes them.
+ * x [S*F*J, C] fp32 (the LayerNorm output), w [3C,C], b [3C] -> out fp32 [S*F*J, C]. */
+int pafuse_qkv_attention(pafuse_ctx* ctx, const float* x, const float* w, const float* b, float* out, int32_t S,
+                         int32_t J, int32_t C, int32_t temporal, void* stream);
+
 /* debugging switch: route the path's GEMMs through the CUDA-core reference kernel */
 int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable);
 /* debugging switch: CUDA-core attention kernel instead of the tcgen05 one */

@@ -48,6 +48,8 @@ _SIGNATURES = {
     "pafuse_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                 c_int32, c_void_p]),
     "pafuse_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "pafuse_qkv_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                       c_void_p]),
     "pafuse_set_debug_simt_gemm": (c_int32, [c_void_p, c_int32]),
     "pafuse_set_gemm_cta_group": (c_int32, [c_int32]),
     "pafuse_set_debug_simt_attention": (c_int32, [c_void_p, c_int32]),
@@ -238,6 +240,14 @@ class NativeContext:
         with torch.cuda.device(self.device):
             check(self.lib.pafuse_attention(self.handle, _ptr(qkv), _ptr(out), S, J, C, 1 if temporal else 0, _stream()),
                   "pafuse_attention")
+        return out
+
+    def qkv_attention(self, x, w, b, S, J, C, temporal):
+        x, w, b = _f32c(x, self.device), _f32c(w, self.device), _f32c(b, self.device)
+        out = torch.empty((x.shape[0], C), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_qkv_attention(self.handle, _ptr(x), _ptr(w), _ptr(b), _ptr(out), S, J, C,
+                                                1 if temporal else 0, _stream()), "pafuse_qkv_attention")
         return out
 
     def set_debug_simt_gemm(self, enable: bool):

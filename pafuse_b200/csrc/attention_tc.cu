@@ -4,22 +4,27 @@
 // The sequences are tiny (24 / 68 / 42 joints, 27 frames) while tcgen05.mma wants M = 128, so a
 // tile packs G whole sequences ("groups") of L rows: body 5x24, face 1x68, hands 3x42 joints of
 // consecutive tokens; 4 joints x 27 frames of one clip-hypothesis for the temporal blocks.  Per
-// (tile, head) the kernel computes the full 128 x 128 score matrix S = Q K^T with three f16x3
-// passes into TMEM, applies a block-diagonal mask (a query only sees the keys of its own
-// group) inside the softmax, writes the un-normalised probabilities back to TMEM as fp16 hi/lo
-// (the A operand of the second MMA is read from tensor memory), and computes O = P V with V as
-// an MN-major shared-memory operand.  The off-diagonal work is wasted tensor math, which is
-// cheap; the CUDA-core version of this kernel spent 28 % of the whole step on 3.3 % of the FLOPs.
+// unit = (tile, head) the kernel computes the 128 x key_cols score matrix S = Q K^T with three
+// f16x3 passes into TMEM, applies a block-diagonal mask (a query only sees the keys of its own
+// group) inside the softmax, writes the un-normalised probabilities as fp16 hi/lo OVER the scores
+// in tensor memory (the A operand of the second MMA is read from TMEM), and computes O = P V with
+// V as an MN-major shared-memory operand.  The off-diagonal work is wasted tensor math, which is
+// cheap next to the CUDA-core version (28 % of the whole step for 3.3 % of the FLOPs).
 //
-// Inputs are the per-head planes the qkv GEMM epilogue writes: fp16 hi/lo arrays
-// [which(q,k,v) * 8 + head][token][hdp] with the head dimension zero-padded to hdp = 64 / 32
-// so that one tile row is exactly one 128- or 64-byte swizzle span.
+// Inputs are the per-head planes the qkv GEMM epilogue writes (EPI_PLANES): fp16 hi/lo arrays
+// [which(q,k,v) * 8 + head][token][hds], hds = head_dim rounded up to 16; the TMA box is HDP = 64 / 32
+// columns wide (one 128- / 64-byte swizzle span per tile row), columns past hds are zero-filled by
+// the TMA unit.
 //
-//   warp 0     TMA producer: Q,K,V hi/lo tiles of one (tile, head) per stage (2 stages)
-//   warp 1     MMA issuer:   S = QK^T (double-buffered in TMEM), O = PV
-//   warp 2     TMEM allocator
-//   warps 4-7  softmax: thread = tile row = TMEM lane; row max / exp2 / sum without shuffles,
-//              P -> TMEM, O -> registers -> 1/sum -> fp16 hi/lo -> global [token, C]
+//   warp 0     TMEM allocator, then TMA producer: one Q/K ring and one V ring, two stages each, so the
+//              next unit's Q,K are in flight while this unit's softmax and PV run
+//   warp 1     MMA issuer:   S = QK^T, O = PV, two units in flight (one per softmax group)
+//   warps 4-7  softmax group 0 (units 0, 2, 4, ... of this CTA), TMEM stage 0
+//   warps 8-11 softmax group 1 (units 1, 3, 5, ...), TMEM stage 1   (setmaxnreg: 232 registers each,
+//              taken from the control warpgroup, so a row's scores fit without spilling)
+//              thread = tile row = TMEM lane: the row's live score columns are read ONCE into registers
+//              (the first version read them twice and was TMEM-read / issue bound), masked max, exp2, sum,
+//              fp16 hi/lo -> TMEM, then O -> registers -> 1/sum -> fp16 hi/lo -> global [token, C]
 #include "kernels.cuh"
 
 #include <cudaTypedefs.h>
@@ -30,18 +35,19 @@ namespace pafuse {
 namespace {
 
 constexpr int TILE_ROWS = 128;
-constexpr int NSTAGE = 2;
-constexpr int ATT_THREADS = 256;
-// TMEM columns
-constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_PHI = 256, TM_PLO = 320, TM_O0 = 384, TM_O1 = 448;
+constexpr int ATT_THREADS = 384;
+constexpr int MAX_CH = 3;            // 32-column score chunks a softmax warp keeps in registers
+// TMEM columns: stage s holds S (fp32, 128 columns) at s*128, overwritten in place by P_hi (64 columns of
+// packed fp16 pairs) and P_lo (next 64); O (fp32, HDP columns) at 256 + s*64
+constexpr uint32_t TM_S = 0, TM_PLO = 64, TM_O = 256;
 
 struct AttnTcParams {
     int num_tiles;
     int L, G;                 // group length and groups per tile (G*L <= 128)
-    int hd, hdp, C;
+    int hd, C;
     int temporal;
     int J, F;
-    int tiles_per_seq;        // temporal: ceil(J / 4)
+    int tiles_per_seq;        // temporal: ceil(J / G)
     long long M;              // valid token rows
     float scale_log2e;        // hd^-0.5 * log2(e)
     op_t* o_hi;
@@ -98,6 +104,15 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+// two probabilities in [0,1] -> packed fp16 hi pair and lo pair (no range clamp needed)
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 template <int HDP>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
@@ -108,43 +123,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     constexpr uint32_t LAYOUT = HDP == 64 ? 2u : 4u;
     constexpr uint32_t SBO = 8 * ROWB;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE];
-    __shared__ __align__(8) uint64_t s_full[2], s_empty[2], o_full[2], o_empty[2], p_full, p_empty;
+    __shared__ __align__(8) uint64_t qk_full[2], qk_empty[2], v_full[2], v_empty[2];
+    __shared__ __align__(8) uint64_t s_full[2], p_full[2], o_full[2], o_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_units = p.num_tiles * 8;
-    const int rows_used = p.G * p.L;                           // tile rows that hold tokens
-    const int load_rows = p.temporal ? rows_used : TILE_ROWS;  // rows each TMA box writes
+    const int n_local = (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int rows_used = p.G * p.L;                           // tile rows that hold tokens (= rows every TMA box writes)
     const int key_steps = (rows_used + 15) / 16;               // 16-key MMA steps that can hold live keys
 
-    // rows a temporal box never writes must not hold NaN bit patterns (0 * NaN in the PV product)
-    for (int i = threadIdx.x; i < NSTAGE * STAGE_BYTES / 16; i += ATT_THREADS)
+    // rows no box ever writes must not hold NaN bit patterns (0 * NaN in the PV product)
+    for (int i = threadIdx.x; i < 2 * STAGE_BYTES / 16; i += ATT_THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 1 && lane == 0) {
         prefetch_tensormap(&tm_hi);
         prefetch_tensormap(&tm_lo);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
         for (int s = 0; s < 2; ++s) {
+            mbar_init(&qk_full[s], 1);
+            mbar_init(&qk_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], 4);
+            mbar_init(&p_full[s], 4);                          // one lane per warp of the stage's softmax group
             mbar_init(&o_full[s], 1);
             mbar_init(&o_empty[s], 4);
         }
-        mbar_init(&p_full, 4);
-        mbar_init(&p_empty, 1);
         fence_barrier_init();
     }
-    if (warp == 2) {
+    if (warp == 0) {
         tmem_alloc<1>(&tmem_base_slot, 512);
         tmem_relinquish<1>();
     }
@@ -153,29 +164,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");                   // control warpgroup donates registers ...
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int it = 0;
-            for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+            const uint32_t tile_tx = (uint32_t)(rows_used * ROWB);
+            for (int it = 0; it < n_local; ++it) {
+                const int u = (int)blockIdx.x + it * (int)gridDim.x;
                 const int stage = it & 1;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 const int tile = u >> 3, head = u & 7;
-                mbar_wait(&empty_bar[stage], ph ^ 1);
                 uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(6 * load_rows * ROWB));
+                int c1, c2;                                    // spatial: (row, -) ; temporal: (s*F, j0)
+                if (!p.temporal) {
+                    c1 = tile * rows_used;
+                    c2 = 0;
+                } else {
+                    c1 = (tile / p.tiles_per_seq) * p.F;
+                    c2 = (tile % p.tiles_per_seq) * p.G;
+                }
 #pragma unroll
                 for (int w = 0; w < 3; ++w) {                  // q, k, v
                     const int plane = w * 8 + head;
+                    uint64_t* bar;
+                    if (w == 0) {
+                        mbar_wait(&qk_empty[stage], ph ^ 1);   // QK^T of the unit that last used this stage has retired
+                        mbar_arrive_expect_tx(&qk_full[stage], 4 * tile_tx);
+                    } else if (w == 2) {
+                        mbar_wait(&v_empty[stage], ph ^ 1);    // PV of that unit has retired
+                        mbar_arrive_expect_tx(&v_full[stage], 2 * tile_tx);
+                    }
+                    bar = w == 2 ? &v_full[stage] : &qk_full[stage];
                     if (!p.temporal) {
-                        const int row0 = tile * rows_used;
-                        tma_load_3d(st + (2 * w) * TILE_BYTES, &tm_hi, &full_bar[stage], 0, row0, plane);
-                        tma_load_3d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, &full_bar[stage], 0, row0, plane);
+                        tma_load_3d(st + (2 * w) * TILE_BYTES, &tm_hi, bar, 0, c1, plane);
+                        tma_load_3d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, bar, 0, c1, plane);
                     } else {
-                        const int s = tile / p.tiles_per_seq;
-                        const int j0 = (tile % p.tiles_per_seq) * p.G;
-                        tma_load_4d(st + (2 * w) * TILE_BYTES, &tm_hi, &full_bar[stage], 0, s * p.F, j0, plane);
-                        tma_load_4d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, &full_bar[stage], 0, s * p.F, j0, plane);
+                        tma_load_4d(st + (2 * w) * TILE_BYTES, &tm_hi, bar, 0, c1, c2, plane);
+                        tma_load_4d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, bar, 0, c1, c2, plane);
                     }
                 }
             }
@@ -183,17 +209,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc_qk = make_idesc_f16(128, 128);
+            const uint32_t idesc_qk = make_idesc_f16(128, (uint32_t)(key_steps * 16));
             const uint32_t idesc_pv = make_idesc_f16(128, HDP) | (1u << 16);      // B (= V) is MN-major
-            const int n_local = (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
             auto issue_qk = [&](int it) {
                 const int stage = it & 1;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(&full_bar[stage], ph);
-                mbar_wait(&s_empty[stage], ph ^ 1);
+                mbar_wait(&qk_full[stage], ph);
                 tcgen05_fence_after();
+                // S[stage] aliases P[stage] of unit it-2: that PV was issued before this point and the
+                // tensor pipe executes in issue order
                 const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                const uint32_t d = tmem_base + (stage ? TM_S1 : TM_S0);
+                const uint32_t d = tmem_base + TM_S + (uint32_t)stage * 128u;
 #pragma unroll
                 for (int k = 0; k < HDP / 16; ++k) {
                     const uint32_t ko = (uint32_t)k * 32u;
@@ -204,121 +230,131 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     umma_f16_ss<1>(d, qh, kl, idesc_qk, 1u);
                     umma_f16_ss<1>(d, qh, kh, idesc_qk, 1u);
                 }
+                umma_commit<1>(&qk_empty[stage]);              // Q,K tiles of this stage may be overwritten
                 umma_commit<1>(&s_full[stage]);
             };
             if (n_local > 0) issue_qk(0);
+            if (n_local > 1) issue_qk(1);
             for (int it = 0; it < n_local; ++it) {
-                if (it + 1 < n_local) issue_qk(it + 1);
                 const int stage = it & 1;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(&p_full, (uint32_t)it & 1u);
-                mbar_wait(&o_empty[stage], ph ^ 1);
+                mbar_wait(&v_full[stage], ph);
+                mbar_wait(&o_empty[stage], ph ^ 1);            // the softmax group has read O of unit it-2
+                mbar_wait(&p_full[stage], ph);                 // P of this unit is in tensor memory
                 tcgen05_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                const uint32_t d = tmem_base + (stage ? TM_O1 : TM_O0);
+                const uint32_t d = tmem_base + TM_O + (uint32_t)stage * 64u;
+                const uint32_t pbase = tmem_base + TM_S + (uint32_t)stage * 128u;
                 for (int k = 0; k < key_steps; ++k) {
                     const uint32_t vo = (uint32_t)k * 16u * ROWB;                 // 16 keys further down the V tile
                     const uint64_t vh = make_desc(sa + 4 * TILE_BYTES + vo, SBO, LAYOUT);
                     const uint64_t vl = make_desc(sa + 5 * TILE_BYTES + vo, SBO, LAYOUT);
-                    const uint32_t ph_a = tmem_base + TM_PHI + (uint32_t)k * 8u;  // 16 fp16 keys = 8 columns
-                    const uint32_t pl_a = tmem_base + TM_PLO + (uint32_t)k * 8u;
+                    const uint32_t ph_a = pbase + (uint32_t)k * 8u;               // 16 fp16 keys = 8 columns
+                    const uint32_t pl_a = pbase + TM_PLO + (uint32_t)k * 8u;
                     umma_f16_ts(d, pl_a, vh, idesc_pv, k != 0 ? 1u : 0u);
                     umma_f16_ts(d, ph_a, vl, idesc_pv, 1u);
                     umma_f16_ts(d, ph_a, vh, idesc_pv, 1u);
                 }
-                umma_commit<1>(&empty_bar[stage]);
-                umma_commit<1>(&p_empty);
+                umma_commit<1>(&v_empty[stage]);
                 umma_commit<1>(&o_full[stage]);
+                if (it + 2 < n_local) issue_qk(it + 2);
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");              // ... to the two softmax warpgroups
         // ===================== softmax + output =====================
-        const int q = warp - 4;
+        const int wg = (warp - 4) >> 2;                        // softmax group = TMEM stage
+        const int q = warp & 3;                                // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;                           // tile row == TMEM lane
         const bool row_live = r < rows_used;
         const int g = row_live ? r / p.L : 0;
-        const int klo = g * p.L, khi = klo + p.L;              // this row's keys
+        const int klo = g * p.L;                               // this row's keys: [klo, klo + Leff)
+        const unsigned Leff = row_live ? (unsigned)p.L : 0u;
         // keys any row of this warp can see (warp-uniform)
         const int w_first = q * 32, w_last = min(q * 32 + 31, rows_used - 1);
-        const int wlo = w_first < rows_used ? (w_first / p.L) * p.L : 0;
-        const int whi = w_first < rows_used ? (w_last / p.L + 1) * p.L : 0;
+        const bool warp_live = w_first < rows_used;
+        const int wlo = warp_live ? (w_first / p.L) * p.L : 0;
+        const int whi = warp_live ? (w_last / p.L + 1) * p.L : 0;
+        const int c_base = wlo >> 5;
+        const int n_ch = warp_live ? ((whi + 31) >> 5) - c_base : 0;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        int it = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
-            const int stage = it & 1;
+        const uint32_t s_addr = tmem_base + lane_sel + TM_S + (uint32_t)wg * 128u;
+        const uint32_t o_addr = tmem_base + lane_sel + TM_O + (uint32_t)wg * 64u;
+        const float sc = p.scale_log2e;
+        for (int it = wg; it < n_local; it += 2) {
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            const int u = (int)blockIdx.x + it * (int)gridDim.x;
             const int tile = u >> 3, head = u & 7;
-            const uint32_t s_addr = tmem_base + lane_sel + (stage ? TM_S1 : TM_S0);
-            mbar_wait(&s_full[stage], ph);
-            tcgen05_fence_after();
-            // ---- pass 1: row maximum over the row's own keys
-            float mx = -INFINITY;
-            for (int c0 = 0; c0 < key_steps * 16; c0 += 32) {
-                if (c0 + 32 <= wlo || c0 >= whi) continue;     // warp-uniform: no live key of this warp in the chunk
-                uint32_t sv[32];
-                tmem_ld_32x32(s_addr + (uint32_t)c0, sv);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int c = c0 + i;
-                    if (c >= klo && c < khi) mx = fmaxf(mx, __uint_as_float(sv[i]));
-                }
-            }
-            if (!row_live) mx = 0.f;
-            const float moff = mx * p.scale_log2e;
-            // ---- pass 2: p = exp2(s*c - m*c), row sum, fp16 hi/lo into TMEM (zeros outside the group)
-            mbar_wait(&p_empty, ((uint32_t)it & 1u) ^ 1u);     // PV of the previous unit has consumed P
+            mbar_wait(&s_full[wg], ph);
             tcgen05_fence_after();
             float sum = 0.f;
-            for (int c0 = 0; c0 < key_steps * 16; c0 += 32) {
-                uint32_t hi16[16], lo16[16];
-                if (c0 + 32 <= wlo || c0 >= whi) {
+            if (warp_live) {
+                // ---- the live score columns of this row, once, into registers: at most MAX_CH 32-column
+                // chunks starting at chunk c_base hold keys any row of this warp may see (host-checked)
+                uint32_t sv[MAX_CH * 32];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) hi16[i] = lo16[i] = 0u;
-                } else {
-                    uint32_t sv[32];
-                    tmem_ld_32x32(s_addr + (uint32_t)c0, sv);
-                    tmem_ld_wait();
+                for (int k = 0; k < MAX_CH; ++k)
+                    if (k < n_ch) tmem_ld_32x32(s_addr + (uint32_t)((c_base + k) * 32), &sv[k * 32]);
+                tmem_ld_wait();
+                // ---- masked row maximum (other groups' keys -> -inf, kept in the registers)
+                float mx = -INFINITY;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float pv[2];
+                for (int k = 0; k < MAX_CH; ++k)
+                    if (k < n_ch) {
+                        const int col0 = (c_base + k) * 32 - klo;
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int c = c0 + 2 * i + e;
-                            float v = 0.f;
-                            if (row_live && c >= klo && c < khi)
-                                v = fast_exp2(fmaf(__uint_as_float(sv[2 * i + e]), p.scale_log2e, -moff));
-                            pv[e] = v;
-                            sum += v;
+                        for (int i = 0; i < 32; ++i) {
+                            const bool mine = (unsigned)(col0 + i) < Leff;
+                            const float v = mine ? __uint_as_float(sv[k * 32 + i]) : -INFINITY;
+                            sv[k * 32 + i] = __float_as_uint(v);
+                            mx = fmaxf(mx, v);
                         }
-                        op_t h0, l0, h1, l1;
-                        split_op(pv[0], h0, l0);
-                        split_op(pv[1], h1, l1);
-                        hi16[i] = pack_op2(h0, h1);
-                        lo16[i] = pack_op2(l0, l1);
                     }
+                const float moff = row_live ? mx * sc : 0.f;
+                // ---- p = exp2(s*c - m*c), row sum, fp16 hi/lo over the scores (zeros outside the group)
+#pragma unroll
+                for (int k = 0; k < MAX_CH; ++k)
+                    if (k < n_ch) {
+                        uint32_t hi16[16], lo16[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[k * 32 + 2 * i]), sc, -moff));
+                            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[k * 32 + 2 * i + 1]), sc, -moff));
+                            sum += p0 + p1;
+                            split_pair(p0, p1, hi16[i], lo16[i]);
+                        }
+                        tmem_st_32x16(s_addr + (uint32_t)((c_base + k) * 16), hi16);
+                        tmem_st_32x16(s_addr + TM_PLO + (uint32_t)((c_base + k) * 16), lo16);
+                    }
+                {
+                    uint32_t z[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) z[i] = 0u;
+                    for (int c = 0; 2 * c < key_steps; ++c)    // chunks the PV product reads but this warp never sees
+                        if (c < c_base || c >= c_base + n_ch) {
+                            tmem_st_32x16(s_addr + (uint32_t)(c * 16), z);
+                            tmem_st_32x16(s_addr + TM_PLO + (uint32_t)(c * 16), z);
+                        }
                 }
-                tmem_st_32x16(tmem_base + lane_sel + TM_PHI + (uint32_t)(c0 >> 1), hi16);
-                tmem_st_32x16(tmem_base + lane_sel + TM_PLO + (uint32_t)(c0 >> 1), lo16);
+                tmem_st_wait();
             }
-            tmem_st_wait();
+            // rows of a dead warp feed garbage into rows of O nobody stores: nothing to write for them
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&p_full);                          // P is in tensor memory
-                mbar_arrive(&s_empty[stage]);                  // S has been read twice, QK of unit it+2 may overwrite it
-            }
+            if (lane == 0) mbar_arrive(&p_full[wg]);
             // ---- output: O / sum -> fp16 hi/lo -> global
-            mbar_wait(&o_full[stage], ph);
+            mbar_wait(&o_full[wg], ph);
             tcgen05_fence_after();
             uint32_t ov[HDP];
-            const uint32_t o_addr = tmem_base + lane_sel + (stage ? TM_O1 : TM_O0);
-            tmem_ld_32x32(o_addr, ov);
-            if (HDP == 64) tmem_ld_32x32(o_addr + 32u, ov + 32);
-            tmem_ld_wait();
+            if (warp_live) {
+                tmem_ld_32x32(o_addr, ov);
+                if (HDP == 64) tmem_ld_32x32(o_addr + 32u, ov + 32);
+                tmem_ld_wait();
+            }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&o_empty[stage]);
+            if (lane == 0) mbar_arrive(&o_empty[wg]);
             long long token = -1;
             if (row_live) {
                 if (!p.temporal) {
@@ -352,7 +388,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 0) {
         tcgen05_fence_after();
         tmem_dealloc<1>(tmem_base, 512);
     }
@@ -377,29 +413,31 @@ int att_init() {
     return 0;
 }
 
-// planes [24][rows_cap][hdp] fp16.  Spatial: (hdp, rows_cap, 24), box (hdp, 128, 1).
-// Temporal: (hdp, S*F [stride J*hdp], J [stride hdp], 24), box (hdp, F, G, 1): the box lands in shared
+// planes [24][rows_cap][hds] fp16; the box is hdp >= hds columns wide (columns past hds are zero-filled).
+// Spatial: (hds, rows_cap, 24), box (hdp, G*L, 1).
+// Temporal: (hds, S*F [stride J*hds], J [stride hds], 24), box (hdp, F, G, 1): the box lands in shared
 // memory joint-major, i.e. as G groups of F consecutive rows.
-int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int hdp, bool temporal, int J, int F, int G) {
+int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int hds, int hdp, bool temporal, int J, int F,
+                   int G, int L) {
     const CUtensorMapSwizzle sw = hdp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r;
     if (!temporal) {
-        cuuint64_t dims[3] = {(cuuint64_t)hdp, (cuuint64_t)rows_cap, 24};
-        cuuint64_t strides[2] = {(cuuint64_t)hdp * 2, (cuuint64_t)rows_cap * hdp * 2};
-        cuuint32_t box[3] = {(cuuint32_t)hdp, TILE_ROWS, 1};
+        cuuint64_t dims[3] = {(cuuint64_t)hds, (cuuint64_t)rows_cap, 24};
+        cuuint64_t strides[2] = {(cuuint64_t)hds * 2, (cuuint64_t)rows_cap * hds * 2};
+        cuuint32_t box[3] = {(cuuint32_t)hdp, (cuuint32_t)(G * L), 1};
         r = g_enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<op_t*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
-        cuuint64_t dims[4] = {(cuuint64_t)hdp, (cuuint64_t)(rows_cap / J), (cuuint64_t)J, 24};
-        cuuint64_t strides[3] = {(cuuint64_t)J * hdp * 2, (cuuint64_t)hdp * 2, (cuuint64_t)rows_cap * hdp * 2};
+        cuuint64_t dims[4] = {(cuuint64_t)hds, (cuuint64_t)(rows_cap / J), (cuuint64_t)J, 24};
+        cuuint64_t strides[3] = {(cuuint64_t)J * hds * 2, (cuuint64_t)hds * 2, (cuuint64_t)rows_cap * hds * 2};
         cuuint32_t box[4] = {(cuuint32_t)hdp, (cuuint32_t)F, (cuuint32_t)G, 1};
         r = g_enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<op_t*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) {
-        set_last_error("cuTensorMapEncodeTiled(attention planes) failed (%d) rows_cap=%lld hdp=%d temporal=%d", (int)r,
-                       rows_cap, hdp, (int)temporal);
+        set_last_error("cuTensorMapEncodeTiled(attention planes) failed (%d) rows_cap=%lld hds=%d hdp=%d temporal=%d", (int)r,
+                       rows_cap, hds, hdp, (int)temporal);
         return -2;
     }
     return 0;
@@ -407,7 +445,7 @@ int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int h
 
 template <int HDP>
 int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, cudaStream_t st) {
-    constexpr int SMEM = NSTAGE * 6 * TILE_ROWS * HDP * 2 + 1024;
+    constexpr int SMEM = 2 * 6 * TILE_ROWS * HDP * 2 + 1024;
     auto kern = attention_tc_kernel<HDP>;
     static bool configured = false;
     if (!configured) {
@@ -423,8 +461,6 @@ int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& 
 
 }  // namespace
 
-int attn_head_pad(int hd) { return hd > 32 ? 64 : 32; }
-
 // groups per 128-row tile
 static int groups_per_tile(int L, bool temporal) { return temporal ? 4 : 128 / L; }
 
@@ -432,9 +468,10 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
                         cudaStream_t st) {
     if (S == 0) return 0;
     if (int rc = att_init()) return rc;
-    const int hd = C / 8, hdp = attn_head_pad(hd);
-    if (hd > 64 || hd % 4 != 0 || (temporal ? F : J) > 128 || pl.hdp != hdp || (temporal && pl.rows_cap % J != 0)) {
-        set_last_error("attention_tc: unsupported shape J=%d F=%d C=%d temporal=%d", J, F, C, temporal);
+    const int hd = C / 8, hds = attn_head_store(hd), hdp = hds > 32 ? 64 : 32;
+    if (hd > 64 || hd % 4 != 0 || (temporal ? F : J) > 128 || (temporal && 4 * F > 128) || pl.hds != hds ||
+        (temporal && pl.rows_cap % J != 0)) {
+        set_last_error("attention_tc: unsupported shape J=%d F=%d C=%d temporal=%d (plane width %d)", J, F, C, temporal, pl.hds);
         return -1;
     }
     AttnTcParams p;
@@ -442,7 +479,6 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
     p.L = temporal ? F : J;
     p.G = groups_per_tile(p.L, temporal != 0);
     p.hd = hd;
-    p.hdp = hdp;
     p.C = C;
     p.J = J;
     p.F = F;
@@ -455,39 +491,47 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
         const long long rows_per_tile = (long long)p.G * p.L;
         p.num_tiles = (int)((p.M + rows_per_tile - 1) / rows_per_tile);
     }
+    for (int w0 = 0; w0 < p.G * p.L; w0 += 32) {            // live key chunks per softmax warp
+        const int w1 = (w0 + 31 < p.G * p.L - 1) ? w0 + 31 : p.G * p.L - 1;
+        const int lo = (w0 / p.L) * p.L, hi = (w1 / p.L + 1) * p.L;
+        if ((hi + 31) / 32 - lo / 32 > MAX_CH) {
+            set_last_error("attention_tc: group length %d needs more than %d score chunks per warp", p.L, MAX_CH);
+            return -1;
+        }
+    }
     p.scale_log2e = (float)(pow((double)hd, -0.5) * 1.4426950408889634);
     p.o_hi = o_hi;
     p.o_lo = o_lo;
     CUtensorMap mh, ml;
-    if (int rc = make_plane_map(&mh, pl.hi, pl.rows_cap, hdp, temporal != 0, J, F, p.G)) return rc;
-    if (int rc = make_plane_map(&ml, pl.lo, pl.rows_cap, hdp, temporal != 0, J, F, p.G)) return rc;
+    if (int rc = make_plane_map(&mh, pl.hi, pl.rows_cap, hds, hdp, temporal != 0, J, F, p.G, p.L)) return rc;
+    if (int rc = make_plane_map(&ml, pl.lo, pl.rows_cap, hds, hdp, temporal != 0, J, F, p.G, p.L)) return rc;
     return hdp == 64 ? launch_tc<64>(mh, ml, p, st) : launch_tc<32>(mh, ml, p, st);
 }
 
 // fp32 qkv [M,3C] -> head planes (unit tests; the production path gets the planes from the qkv GEMM epilogue)
 __global__ void qkv_to_planes_kernel(const float* __restrict__ qkv, op_t* __restrict__ hi, op_t* __restrict__ lo,
-                                     long long M, long long rows_cap, int C, int hd, int hdp) {
+                                     long long M, long long rows_cap, int C, int hd, int hds) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = M * 24 * hdp;
+    const long long total = M * 24 * hds;
     if (idx >= total) return;
-    const int d = (int)(idx % hdp);
-    long long t = idx / hdp;
+    const int d = (int)(idx % hds);
+    long long t = idx / hds;
     const long long m = t % M;
     const int plane = (int)(t / M);
     float v = 0.f;
     if (d < hd) v = qkv[(size_t)m * 3 * C + (plane / 8) * C + (plane % 8) * hd + d];
     op_t h, l;
     split_op(v, h, l);
-    const size_t o = ((size_t)plane * rows_cap + m) * hdp + d;
+    const size_t o = ((size_t)plane * rows_cap + m) * hds + d;
     hi[o] = h;
     lo[o] = l;
 }
 
 int launch_qkv_to_planes(const float* qkv, const AttnPlanes& pl, long long M, int C, cudaStream_t st) {
     const int hd = C / 8;
-    const long long total = M * 24 * pl.hdp;
+    const long long total = M * 24 * pl.hds;
     if (total == 0) return 0;
-    qkv_to_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(qkv, pl.hi, pl.lo, M, pl.rows_cap, C, hd, pl.hdp);
+    qkv_to_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(qkv, pl.hi, pl.lo, M, pl.rows_cap, C, hd, pl.hds);
     PAFUSE_LAUNCH_OK();
     return 0;
 }

@@ -30,6 +30,28 @@ int launch_split_weights(const float* w, op_t* hi, op_t* lo, size_t n, cudaStrea
     return 0;
 }
 
+// qkv weight [3C,C] (rows [q|k|v], head-major, mixste.py:65) -> [24*hds, C]: row (plane, d) = source row
+// plane*hd + d for d < hd, zero otherwise (plane = which*8 + head).  With zero weight rows and zero bias the
+// pad columns of the GEMM output are exact zeros, which is what the attention tiles need.
+__global__ void pack_qkv_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wp,
+                                float* __restrict__ bp, int C, int hd, int hds) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)24 * hds * C;
+    if (i >= total) return;
+    int k = (int)(i % C);
+    int row = (int)(i / C);
+    int plane = row / hds, d = row % hds;
+    wp[i] = d < hd ? w[(size_t)(plane * hd + d) * C + k] : 0.f;
+    if (k == 0) bp[row] = d < hd ? b[plane * hd + d] : 0.f;
+}
+
+int launch_pack_qkv(const float* w, const float* b, float* wp, float* bp, int C, int hd, int hds, cudaStream_t st) {
+    size_t total = (size_t)24 * hds * C;
+    pack_qkv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, b, wp, bp, C, hd, hds);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
 // ------------------------------------------------------------------ time MLP
 // temb = W2 * gelu(W1 * sinus + b1) + b2      (mixste.py:179-184); one CTA per part-call.
 __global__ void time_mlp_kernel(const float* __restrict__ sinus, const float* __restrict__ w1,

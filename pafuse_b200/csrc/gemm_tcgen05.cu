@@ -55,6 +55,8 @@ struct KernelParams {
     int stage_bytes;                 // per CTA
     float out_scale;                 // undoes WEIGHT_SCALE
     const float* bias;
+    int hds;                         // EPI_PLANES: stored head width (columns per plane)
+    int plane_pw;                    // EPI_PLANES: columns per output box, 32 (hds % 32 == 0) or 16
 };
 
 template <int EPI, int CG>
@@ -91,7 +93,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         prefetch_tensormap(&tm_w_hi);
         prefetch_tensormap(&tm_w_lo);
         prefetch_tensormap(&tm_out0);
-        if (EPI == EPI_GELU_SPLIT) prefetch_tensormap(&tm_out1);
+        if (EPI == EPI_GELU_SPLIT || EPI == EPI_PLANES) prefetch_tensormap(&tm_out1);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -241,33 +243,52 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         bulk_commit_group();
                     }
                 } else {
-                    // two boxes of 32 rows x 64 B (hi, lo), 64-byte swizzle: chunk i of row r at i ^ ((r >> 1) & 3)
-                    uint8_t* rowh = box + lane * 64;
-                    uint8_t* rowl = rowh + 2048;
+                    // fp16 hi/lo outputs.  Wide boxes (GELU_SPLIT, PLANES with 32-column heads): two boxes of
+                    // 32 rows x 64 B (hi, lo), 64-byte swizzle: chunk i of row r at i ^ ((r >> 1) & 3).
+                    // Narrow boxes (PLANES with 48-column heads): per 16-column piece p one box of 32 rows x 32 B,
+                    // unswizzled, hi at p * 1024 and lo at 2048 + p * 1024.
+                    const bool narrow = EPI == EPI_PLANES && p.plane_pw == 16;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float4 b0 = __ldg(b4 + 2 * i), b1 = __ldg(b4 + 2 * i + 1);
                         float v[8];
-                        v[0] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 0]), oscale, b0.x));
-                        v[1] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 1]), oscale, b0.y));
-                        v[2] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 2]), oscale, b0.z));
-                        v[3] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 3]), oscale, b0.w));
-                        v[4] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 4]), oscale, b1.x));
-                        v[5] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 5]), oscale, b1.y));
-                        v[6] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 6]), oscale, b1.z));
-                        v[7] = gelu_erf(fmaf(__uint_as_float(r[8 * i + 7]), oscale, b1.w));
+                        v[0] = fmaf(__uint_as_float(r[8 * i + 0]), oscale, b0.x);
+                        v[1] = fmaf(__uint_as_float(r[8 * i + 1]), oscale, b0.y);
+                        v[2] = fmaf(__uint_as_float(r[8 * i + 2]), oscale, b0.z);
+                        v[3] = fmaf(__uint_as_float(r[8 * i + 3]), oscale, b0.w);
+                        v[4] = fmaf(__uint_as_float(r[8 * i + 4]), oscale, b1.x);
+                        v[5] = fmaf(__uint_as_float(r[8 * i + 5]), oscale, b1.y);
+                        v[6] = fmaf(__uint_as_float(r[8 * i + 6]), oscale, b1.z);
+                        v[7] = fmaf(__uint_as_float(r[8 * i + 7]), oscale, b1.w);
+                        if (EPI == EPI_GELU_SPLIT) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+                        }
                         uint2 h0, l0, h1, l1;
                         split4(v, h0, l0);
                         split4(v + 4, h1, l1);
-                        const int off = (i ^ ((lane >> 1) & 3)) << 4;
-                        *reinterpret_cast<uint4*>(rowh + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                        *reinterpret_cast<uint4*>(rowl + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                        const int off = narrow ? (i >> 1) * 1024 + lane * 32 + (i & 1) * 16
+                                               : lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);
+                        *reinterpret_cast<uint4*>(box + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                        *reinterpret_cast<uint4*>(box + 2048 + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tm_out0, box, col, row0);
-                        tma_store_2d(&tm_out1, box + 2048, col, row0);
+                        if (EPI == EPI_GELU_SPLIT) {
+                            tma_store_2d(&tm_out0, box, col, row0);
+                            tma_store_2d(&tm_out1, box + 2048, col, row0);
+                        } else if (!narrow) {
+                            tma_store_3d(&tm_out0, box, 0, row0, col / 32);
+                            tma_store_3d(&tm_out1, box + 2048, 0, row0, col / 32);
+                        } else {
+#pragma unroll
+                            for (int pc = 0; pc < 2; ++pc) {
+                                const int cp = col + 16 * pc;
+                                tma_store_3d(&tm_out0, box + pc * 1024, cp % p.hds, row0, cp / p.hds);
+                                tma_store_3d(&tm_out1, box + 2048 + pc * 1024, cp % p.hds, row0, cp / p.hds);
+                            }
+                        }
                         bulk_commit_group();
                     }
                 }
@@ -318,6 +339,22 @@ int make_map_out(CUtensorMap* map, const void* ptr, long long rows, int N, bool 
                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled(out) failed (%d) rows=%lld N=%d ptr=%p", (int)r, rows, N, ptr);
+        return -2;
+    }
+    return 0;
+}
+
+// head planes [24][rows_cap][hds] fp16: box = pw columns x 32 rows of one plane
+int make_map_planes(CUtensorMap* map, const void* ptr, long long rows_cap, int hds, int pw) {
+    cuuint64_t dims[3] = {(cuuint64_t)hds, (cuuint64_t)rows_cap, 24};
+    cuuint64_t strides[2] = {(cuuint64_t)hds * 2, (cuuint64_t)rows_cap * hds * 2};
+    cuuint32_t box[3] = {(cuuint32_t)pw, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, pw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(planes) failed (%d) rows_cap=%lld hds=%d ptr=%p", (int)r, rows_cap, hds, ptr);
         return -2;
     }
     return 0;
@@ -379,8 +416,17 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     kp.stages = stages;
     kp.out_scale = g.out_scale;
     kp.bias = g.bias;
+    kp.hds = g.planes.hds;
+    kp.plane_pw = g.planes.hds % 32 == 0 ? 32 : 16;
     CUtensorMap o0, o1;
-    if (g.epilogue == EPI_GELU_SPLIT) {
+    if (g.epilogue == EPI_PLANES) {
+        if (g.planes.hds < 16 || g.planes.hds % 16 != 0 || g.N != 24 * g.planes.hds || g.planes.rows_cap < g.M) {
+            set_last_error("gemm: bad head planes (hds=%d N=%d rows_cap=%lld M=%lld)", g.planes.hds, g.N, g.planes.rows_cap, g.M);
+            return -1;
+        }
+        if (int rc = make_map_planes(&o0, g.planes.hi, g.planes.rows_cap, g.planes.hds, kp.plane_pw)) return rc;
+        if (int rc = make_map_planes(&o1, g.planes.lo, g.planes.rows_cap, g.planes.hds, kp.plane_pw)) return rc;
+    } else if (g.epilogue == EPI_GELU_SPLIT) {
         if (int rc = make_map_out(&o0, g.out_hi, g.M, g.N, false)) return rc;
         if (int rc = make_map_out(&o1, g.out_lo, g.M, g.N, false)) return rc;
     } else {
@@ -395,6 +441,7 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
         case EPI_F32: return launch_epi<EPI_F32, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
         case EPI_GELU_SPLIT: return launch_epi<EPI_GELU_SPLIT, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
         case EPI_RESID: return launch_epi<EPI_RESID, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
+        case EPI_PLANES: return launch_epi<EPI_PLANES, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
     }
     set_last_error("gemm: bad epilogue %d", g.epilogue);
     return -1;
@@ -453,7 +500,13 @@ __global__ void gemm_simt_kernel(GemmArgs g) {
     for (int k = 0; k < g.K; ++k) acc = fmaf(join_op(ah[k], al[k]), join_op(wh[k], wl[k]), acc);
     float v = fmaf(acc, g.out_scale, g.bias[n]);
     size_t o = (size_t)m * g.N + n;
-    if (g.epilogue == EPI_F32) {
+    if (g.epilogue == EPI_PLANES) {
+        op_t h, l;
+        split_op(v, h, l);
+        size_t po = ((size_t)(n / g.planes.hds) * g.planes.rows_cap + m) * g.planes.hds + n % g.planes.hds;
+        g.planes.hi[po] = h;
+        g.planes.lo[po] = l;
+    } else if (g.epilogue == EPI_F32) {
         g.out_f32[o] = v;
     } else if (g.epilogue == EPI_RESID) {
         g.out_f32[o] += v;

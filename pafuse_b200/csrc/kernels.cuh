@@ -86,15 +86,17 @@ struct AttnParams {
     float scale;              // head_dim^-0.5, set by launch_attention
 };
 
-// q/k/v of one part as per-head planes [which*8 + head][rows_cap][hdp], fp16 hi/lo (attention_tc.cu)
+// q/k/v of one part as per-head planes [which*8 + head][rows_cap][hds], fp16 hi/lo: written by the
+// qkv GEMM epilogue (EPI_PLANES), read by attention_tc.cu
 struct AttnPlanes {
     op_t* hi;
     op_t* lo;
     long long rows_cap;       // rows per plane (multiple of J)
-    int hdp;                  // head dim padded to 64 / 32
+    int hds;                  // stored head width = head_dim rounded up to 16 (48 / 32 / 32); pad columns are zero
 };
+inline int attn_head_store(int hd) { return (hd + 15) / 16 * 16; }
 
-enum GemmEpilogue { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_RESID = 2 };
+enum GemmEpilogue { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_RESID = 2, EPI_PLANES = 3 };
 
 struct GemmArgs {
     const op_t *a_hi, *a_lo;   // [M,K]
@@ -106,6 +108,8 @@ struct GemmArgs {
     int N, K;
     int epilogue;
     float out_scale = WEIGHT_UNSCALE;   // accumulator scale applied before the bias (weights are stored pre-scaled)
+    // EPI_PLANES: N = 24*hds output columns in plane order (column n -> plane n / hds, d = n % hds)
+    AttnPlanes planes = {nullptr, nullptr, 0, 0};
 };
 
 int launch_split_weights(const float* w, op_t* hi, op_t* lo, size_t n, cudaStream_t st);
@@ -122,10 +126,11 @@ int launch_project(const float* X, const float* cam, float* out, long long npts,
                    cudaStream_t st);
 int launch_aggregate(const AggParams& p, cudaStream_t st);
 int launch_attention(const AttnParams& p, cudaStream_t st);          // CUDA-core version (debug reference)
-int attn_head_pad(int hd);
 int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int F, int J, int C, int temporal,
                         cudaStream_t st);
 int launch_qkv_to_planes(const float* qkv, const AttnPlanes& pl, long long M, int C, cudaStream_t st);
+// qkv weight [3C,C] / bias [3C] -> plane order with every head padded to hds rows (zero rows / zero bias)
+int launch_pack_qkv(const float* w, const float* b, float* wp, float* bp, int C, int hd, int hds, cudaStream_t st);
 
 // tcgen05 GEMM (f16x3 split precision).  Tensor maps are built per call from the raw pointers.
 int gemm_init();                                            // resolves cuTensorMapEncodeTiled

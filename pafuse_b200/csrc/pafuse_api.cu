@@ -29,6 +29,7 @@ struct Slot {
     size_t numel = 0;
     bool gemm = false;   // needs a fp16 hi/lo copy
     bool set = false;
+    bool derived = false;// filled by pafuse_commit_weights, not by the caller
 };
 
 struct Part {
@@ -51,8 +52,8 @@ struct Workspace {
     size_t plane_halves = 0;
     float* x = nullptr;
     op_t *a_hi = nullptr, *a_lo = nullptr;
-    float* qkv = nullptr;
-    op_t *pl_hi = nullptr, *pl_lo = nullptr;   // q/k/v head planes, 24 * rows * 64 halves each
+    float* qkv = nullptr;                      // fp32 qkv: only for the CUDA-core debug attention
+    op_t *pl_hi = nullptr, *pl_lo = nullptr;   // q/k/v head planes, 24 * rows * hds halves each
     op_t *o_hi = nullptr, *o_lo = nullptr;
     op_t *h_hi = nullptr, *h_lo = nullptr;
 };
@@ -127,11 +128,12 @@ struct ProfScope {
     }
 };
 
-void add_slot(Part& p, const std::string& name, size_t numel, bool gemm = false) {
+void add_slot(Part& p, const std::string& name, size_t numel, bool gemm = false, bool derived = false) {
     Slot s;
     s.off = p.total;
     s.numel = numel;
     s.gemm = gemm;
+    s.derived = derived;
     p.slots[name] = s;
     p.total += (numel + 63) / 64 * 64;   // 256-byte alignment (TMA needs 16 B on the bf16 copies)
 }
@@ -165,6 +167,10 @@ void build_part_table(Part& p, int C, int J, int F, int depth) {
             add_slot(p, b + "norm1.bias", c);
             add_slot(p, b + "attn.qkv.weight", 3 * c * c, true);
             add_slot(p, b + "attn.qkv.bias", 3 * c);
+            // plane-ordered, head-padded copies the production qkv GEMM reads (launch_pack_qkv)
+            const size_t hds = (size_t)attn_head_store(C / 8);
+            add_slot(p, b + "attn.qkv.weight_planes", 24 * hds * c, true, true);
+            add_slot(p, b + "attn.qkv.bias_planes", 24 * hds, false, true);
             add_slot(p, b + "attn.proj.weight", c * c, true);
             add_slot(p, b + "attn.proj.bias", c);
             add_slot(p, b + "norm2.weight", c);
@@ -191,12 +197,10 @@ int ensure_workspace(pafuse_ctx* ctx, long long rows_x_c) {
     size_t n = (size_t)rows_x_c;
     if (dev_alloc(&w.x, n)) return PAFUSE_E_CUDA;
     if (dev_alloc(&w.a_hi, n) || dev_alloc(&w.a_lo, n)) return PAFUSE_E_CUDA;
-    if (dev_alloc(&w.qkv, 3 * n)) return PAFUSE_E_CUDA;
-    // planes: rows * 24 * hdp halves with rows*C = n and hdp <= 64 = 8*hdp/C * ... -> 24*64/(8*28) * n upper bound
-    w.plane_halves = (size_t)((double)n * 24.0 * 64.0 / 224.0) + 4096;
+    if (ctx->debug_simt_attn && dev_alloc(&w.qkv, 3 * n)) return PAFUSE_E_CUDA;
+    // planes: rows * 24 * hds halves with rows * C = n: 3 * hds / hd * n, and hds / hd <= 16/13 for hd >= 4... bound by 4 * n
+    w.plane_halves = 4 * n + 4096;
     if (dev_alloc(&w.pl_hi, w.plane_halves) || dev_alloc(&w.pl_lo, w.plane_halves)) return PAFUSE_E_CUDA;
-    PAFUSE_CUDA_OK(cudaMemset(w.pl_hi, 0, w.plane_halves * sizeof(op_t)));
-    PAFUSE_CUDA_OK(cudaMemset(w.pl_lo, 0, w.plane_halves * sizeof(op_t)));
     if (dev_alloc(&w.o_hi, n) || dev_alloc(&w.o_lo, n)) return PAFUSE_E_CUDA;
     if (dev_alloc(&w.h_hi, 2 * n) || dev_alloc(&w.h_lo, 2 * n)) return PAFUSE_E_CUDA;
     w.rows_x_c = rows_x_c;
@@ -293,30 +297,42 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
 
                 GemmArgs g;
                 g.a_hi = w.a_hi; g.a_lo = w.a_lo;
-                g.w_hi = p.wh(b + "attn.qkv.weight"); g.w_lo = p.wl(b + "attn.qkv.weight");
-                g.bias = p.w(b + "attn.qkv.bias");
-                g.out_f32 = w.qkv; g.out_hi = g.out_lo = nullptr;
-                g.M = M; g.N = 3 * C; g.K = C; g.epilogue = EPI_F32;
-                if (int rc = run_gemm(ctx, g, st)) return rc;
-
-                AttnParams a;
-                a.qkv = w.qkv; a.out_hi = w.o_hi; a.out_lo = w.o_lo;
-                a.S = Sc; a.F = F; a.J = J; a.C = C; a.temporal = temporal ? 1 : 0; a.scale = 0.f;
-                {
-                    const double L = temporal ? (double)F : (double)J;
-                    ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st);
-                    if (ctx->debug_simt_attn) {
-                        if (int rc = launch_attention(a, st)) return rc;
-                    } else {
-                        AttnPlanes pl;
-                        pl.hi = w.pl_hi; pl.lo = w.pl_lo; pl.rows_cap = M; pl.hdp = attn_head_pad(C / 8);
-                        if ((size_t)24 * M * pl.hdp > w.plane_halves) {
-                            set_last_error("attention plane workspace too small");
-                            return PAFUSE_E_STATE;
-                        }
-                        if (int rc = launch_qkv_to_planes(w.qkv, pl, M, C, st)) return rc;
-                        if (int rc = launch_attention_tc(pl, w.o_hi, w.o_lo, Sc, F, J, C, temporal ? 1 : 0, st)) return rc;
+                g.M = M; g.K = C;
+                const double L = temporal ? (double)F : (double)J;
+                if (ctx->debug_simt_attn) {
+                    // debug: fp32 qkv + CUDA-core attention
+                    if (!w.qkv) {
+                        set_last_error("debug attention must be selected before the first pass (workspace has no fp32 qkv)");
+                        return PAFUSE_E_STATE;
                     }
+                    g.w_hi = p.wh(b + "attn.qkv.weight"); g.w_lo = p.wl(b + "attn.qkv.weight");
+                    g.bias = p.w(b + "attn.qkv.bias");
+                    g.out_f32 = w.qkv; g.out_hi = g.out_lo = nullptr;
+                    g.N = 3 * C; g.epilogue = EPI_F32;
+                    if (int rc = run_gemm(ctx, g, st)) return rc;
+                    AttnParams a;
+                    a.qkv = w.qkv; a.out_hi = w.o_hi; a.out_lo = w.o_lo;
+                    a.S = Sc; a.F = F; a.J = J; a.C = C; a.temporal = temporal ? 1 : 0; a.scale = 0.f;
+                    ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st);
+                    if (int rc = launch_attention(a, st)) return rc;
+                } else {
+                    // the qkv GEMM writes the fp16 hi/lo head planes the attention kernel loads
+                    AttnPlanes pl;
+                    pl.hi = w.pl_hi; pl.lo = w.pl_lo; pl.rows_cap = M; pl.hds = attn_head_store(C / 8);
+                    if ((size_t)24 * M * pl.hds > w.plane_halves) {
+                        set_last_error("attention plane workspace too small");
+                        return PAFUSE_E_STATE;
+                    }
+                    g.w_hi = p.wh(b + "attn.qkv.weight_planes"); g.w_lo = p.wl(b + "attn.qkv.weight_planes");
+                    g.bias = p.w(b + "attn.qkv.bias_planes");
+                    g.out_f32 = nullptr; g.out_hi = g.out_lo = nullptr;
+                    g.N = 24 * pl.hds; g.epilogue = EPI_PLANES; g.planes = pl;
+                    {
+                        ProfScope ps(ctx, CAT_GEMM, 2.0 * (double)M * 3 * C * C, st);   // algorithmic N = 3C (pad columns not counted)
+                        if (int rc = ctx->debug_simt ? launch_gemm_simt(g, st) : launch_gemm_tcgen05(g, st)) return rc;
+                    }
+                    ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st);
+                    if (int rc = launch_attention_tc(pl, w.o_hi, w.o_lo, Sc, F, J, C, temporal ? 1 : 0, st)) return rc;
                 }
 
                 g.a_hi = w.o_hi; g.a_lo = w.o_lo;
@@ -453,7 +469,7 @@ int pafuse_set_weight(pafuse_ctx* ctx, int32_t part, const char* name, const flo
     }
     Part& p = ctx->parts[part];
     auto it = p.slots.find(name);
-    if (it == p.slots.end()) {
+    if (it == p.slots.end() || it->second.derived) {
         set_last_error("pafuse_set_weight: unknown tensor '%s'", name);
         return PAFUSE_E_ARG;
     }
@@ -474,10 +490,22 @@ int pafuse_commit_weights(pafuse_ctx* ctx, void* stream) {
     for (int pi = 0; pi < ctx->num_parts; ++pi) {
         Part& p = ctx->parts[pi];
         for (auto& kv : p.slots) {
-            if (!kv.second.set) {
+            if (!kv.second.set && !kv.second.derived) {
                 set_last_error("pafuse_commit_weights: part %d tensor '%s' was never set", pi, kv.first.c_str());
                 return PAFUSE_E_STATE;
             }
+        }
+        const char* stacks[2] = {"STEblocks.", "TTEblocks."};
+        for (int sk = 0; sk < 2; ++sk)
+            for (int i = 0; i < ctx->cfg.depth; ++i) {
+                const std::string b = std::string(stacks[sk]) + std::to_string(i) + ".attn.qkv.";
+                if (int rc = launch_pack_qkv(p.f32 + p.slots.at(b + "weight").off, p.f32 + p.slots.at(b + "bias").off,
+                                             p.f32 + p.slots.at(b + "weight_planes").off,
+                                             p.f32 + p.slots.at(b + "bias_planes").off, p.C, p.C / 8,
+                                             attn_head_store(p.C / 8), st))
+                    return rc;
+            }
+        for (auto& kv : p.slots) {
             if (kv.second.gemm)
                 if (int rc = launch_split_weights(p.f32 + kv.second.off, p.hi + kv.second.off, p.lo + kv.second.off,
                                                   kv.second.numel, st))
@@ -598,6 +626,7 @@ int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable) {
 int pafuse_set_debug_simt_attention(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->debug_simt_attn = enable != 0;
+    ctx->ws.rows_x_c = 0;        // the fp32 qkv buffer exists only in debug mode: force a re-allocation
     return 0;
 }
 
@@ -709,9 +738,9 @@ int pafuse_attention(pafuse_ctx* ctx, const float* qkv, float* out, int32_t S, i
             rc = launch_attention(a, st);
         } else {
             AttnPlanes planes;
-            planes.hdp = attn_head_pad(C / 8);
+            planes.hds = attn_head_store(C / 8);
             planes.rows_cap = M;
-            size_t halves = (size_t)24 * M * planes.hdp;
+            size_t halves = (size_t)24 * M * planes.hds;
             if (dev_alloc(&ph, halves) || dev_alloc(&pl, halves)) rc = PAFUSE_E_CUDA;
             planes.hi = ph; planes.lo = pl;
             if (!rc) rc = launch_qkv_to_planes(qkv, planes, M, C, st);
@@ -723,6 +752,46 @@ int pafuse_attention(pafuse_ctx* ctx, const float* qkv, float* out, int32_t S, i
     cudaFree(oh); cudaFree(ol); cudaFree(ph); cudaFree(pl);
     if (!rc && e != cudaSuccess) {
         set_last_error("pafuse_attention: %s", cudaGetErrorString(e));
+        rc = PAFUSE_E_CUDA;
+    }
+    return rc;
+}
+
+int pafuse_qkv_attention(pafuse_ctx* ctx, const float* x, const float* w, const float* b, float* out, int32_t S,
+                         int32_t J, int32_t C, int32_t temporal, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!x || !w || !b || !out || S < 1 || J < 1 || C < 8 || C % 8 != 0) {
+        set_last_error("pafuse_qkv_attention: bad argument");
+        return PAFUSE_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long M = (long long)S * ctx->cfg.frames * J;
+    const int hd = C / 8, hds = attn_head_store(hd);
+    const size_t n = (size_t)M * C, nw = (size_t)24 * hds * C, halves = (size_t)24 * M * hds;
+    op_t *xh = nullptr, *xl = nullptr, *wh = nullptr, *wl = nullptr, *ph = nullptr, *pl = nullptr, *oh = nullptr, *ol = nullptr;
+    float *wp = nullptr, *bp = nullptr;
+    int rc = 0;
+    if (dev_alloc(&xh, n) || dev_alloc(&xl, n) || dev_alloc(&wh, nw) || dev_alloc(&wl, nw) || dev_alloc(&ph, halves) ||
+        dev_alloc(&pl, halves) || dev_alloc(&oh, n) || dev_alloc(&ol, n) || dev_alloc(&wp, nw) ||
+        dev_alloc(&bp, (size_t)24 * hds))
+        rc = PAFUSE_E_CUDA;
+    if (!rc) rc = launch_pack_qkv(w, b, wp, bp, C, hd, hds, st);
+    if (!rc) {
+        split_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, xh, xl, n, 1.0f);
+        split_rows_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(wp, wh, wl, nw, WEIGHT_SCALE);
+        GemmArgs g;
+        g.a_hi = xh; g.a_lo = xl; g.w_hi = wh; g.w_lo = wl; g.bias = bp; g.out_f32 = nullptr; g.out_hi = g.out_lo = nullptr;
+        g.M = M; g.N = 24 * hds; g.K = C; g.epilogue = EPI_PLANES;
+        g.planes.hi = ph; g.planes.lo = pl; g.planes.rows_cap = M; g.planes.hds = hds;
+        rc = ctx->debug_simt ? launch_gemm_simt(g, st) : launch_gemm_tcgen05(g, st);
+        if (!rc) rc = launch_attention_tc(g.planes, oh, ol, S, ctx->cfg.frames, J, C, temporal, st);
+        if (!rc) join_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(oh, ol, out, n);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(xh); cudaFree(xl); cudaFree(wh); cudaFree(wl); cudaFree(ph); cudaFree(pl); cudaFree(oh); cudaFree(ol);
+    cudaFree(wp); cudaFree(bp);
+    if (!rc && e != cudaSuccess) {
+        set_last_error("pafuse_qkv_attention: %s", cudaGetErrorString(e));
         rc = PAFUSE_E_CUDA;
     }
     return rc;

@@ -133,16 +133,44 @@ def test_tensor_core_gemm_equals_cuda_core_gemm_on_the_whole_model():
     assert (a - b).abs().max().item() < 3e-5
 
 
-def test_workspace_chunking_is_invisible():
-    """max_seqs smaller than the sequence count must give bit-identical results (rows are independent)."""
+@pytest.mark.parametrize("max_seqs", [1, 3])
+def test_workspace_chunking_is_invisible(max_seqs):
+    """max_seqs smaller than the sequence count must not change the result.  Rows are independent, but the
+    tcgen05 attention packs several short sequences into one 128-row tile, so the position of a sequence in
+    its tile (hence the order in which the tensor core adds the zero contributions of the other groups) moves
+    with the chunk boundaries: equal to fp32 summation-order noise, not bit-equal."""
     from pafuse_testlib import build_case
     c = build_case("small_B2_H2_K3")
     full = _model(c)(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
     m = _model(c)
-    m.max_seqs = 3
+    m.max_seqs = max_seqs
     m._native_dirty = True
     chunked = m(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
-    assert torch.equal(full, chunked)
+    assert (full - chunked).abs().max().item() < 5e-6
+    rerun = _model(c)(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
+    assert torch.equal(full, rerun)                                   # same launch geometry -> bit-identical
+
+
+@pytest.mark.parametrize("J,C", [(24, 384), (68, 224), (42, 256)])
+@pytest.mark.parametrize("temporal", [False, True])
+def test_qkv_gemm_head_plane_epilogue_feeds_attention(J, C, temporal):
+    """qkv GEMM (head-plane epilogue) + tcgen05 attention == softmax(q k^T / sqrt(hd)) v of mixste.py:63-79."""
+    torch.manual_seed(J * 3 + C + int(temporal))
+    c = _ctx()
+    S, F, hd = 7, 27, C // 8
+    M = S * F * J
+    x = torch.randn(M, C, device="cuda")
+    w = (torch.rand(3 * C, C, device="cuda") * 2 - 1) / C ** 0.5 * 2
+    b = torch.randn(3 * C, device="cuda") * 0.1
+    out = c.qkv_attention(x, w, b, S, J, C, temporal)
+    qkv = x.double() @ w.double().t() + b.double()
+    t = qkv.reshape(S, F, J, 3, 8, hd)
+    q, k, v = t[..., 0, :, :], t[..., 1, :, :], t[..., 2, :, :]
+    perm = (0, 2, 3, 1, 4) if temporal else (0, 1, 3, 2, 4)
+    q, k, v = (z.permute(*perm) for z in (q, k, v))
+    a = torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, dim=-1) @ v
+    a = a.permute(0, 3, 1, 2, 4) if temporal else a.permute(0, 1, 3, 2, 4)
+    assert (out.double() - a.reshape(M, C)).abs().max().item() < 5e-5
 
 
 def test_default_noise_path_is_deterministic_and_finite():

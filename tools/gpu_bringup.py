@@ -169,6 +169,31 @@ def attention_tc_big():
 
 
 @rung
+def qkv_attention():
+    import torch
+    torch.manual_seed(0)
+    c = _ctx()
+    for (J, C) in [(42, 256), (68, 224), (24, 384)]:
+        for temporal in (False, True):
+            S, F, hd = 7, 27, C // 8
+            M = S * F * J
+            x = torch.randn(M, C, device="cuda")
+            w = (torch.rand(3 * C, C, device="cuda") * 2 - 1) / C ** 0.5 * 2
+            b = torch.randn(3 * C, device="cuda") * 0.1
+            out = c.qkv_attention(x, w, b, S, J, C, temporal)
+            torch.cuda.synchronize()
+            t = (x.double() @ w.double().t() + b.double()).reshape(S, F, J, 3, 8, hd)
+            q, k, v = t[..., 0, :, :], t[..., 1, :, :], t[..., 2, :, :]
+            perm = (0, 2, 3, 1, 4) if temporal else (0, 1, 3, 2, 4)
+            q, k, v = (z.permute(*perm) for z in (q, k, v))
+            a = torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, dim=-1) @ v
+            a = a.permute(0, 3, 1, 2, 4) if temporal else a.permute(0, 1, 3, 2, 4)
+            err = (out.double() - a.reshape(M, C)).abs().max().item()
+            print(f"qkv_attention J={J} C={C} temporal={temporal}: max abs err {err:.3e}", flush=True)
+            assert err < 5e-5
+
+
+@rung
 def model_small():
     import numpy as np
     import torch
