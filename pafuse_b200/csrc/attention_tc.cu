@@ -2,29 +2,33 @@
 // sm_100a tensor cores.
 //
 // The sequences are tiny (24 / 68 / 42 joints, 27 frames) while tcgen05.mma wants M = 128, so a
-// tile packs G whole sequences ("groups") of L rows: body 5x24, face 1x68, hands 3x42 joints of
-// consecutive tokens; 4 joints x 27 frames of one clip-hypothesis for the temporal blocks.  Per
-// unit = (tile, head) the kernel computes the 128 x key_cols score matrix S = Q K^T with three
-// f16x3 passes into TMEM, applies a block-diagonal mask (a query only sees the keys of its own
-// group) inside the softmax, writes the un-normalised probabilities as fp16 hi/lo OVER the scores
-// in tensor memory (the A operand of the second MMA is read from TMEM), and computes O = P V with
-// V as an MN-major shared-memory operand.  The off-diagonal work is wasted tensor math, which is
-// cheap next to the CUDA-core version (28 % of the whole step for 3.3 % of the FLOPs).
+// tile packs G whole sequences ("groups"), each padded to Lp = L rounded up to 32 rows:
+// body 4 x (24 -> 32), face 1 x (68 -> 96), hands 2 x (42 -> 64) joints of consecutive (clip, hypothesis,
+// frame) sequences; 4 joints x (27 -> 32) frames of one clip-hypothesis for the temporal blocks.  The
+// padding costs nothing in HBM: the TMA box is Lp rows long in a tensor dimension of extent L, the
+// rows past L are zero-filled by the TMA unit.  With 32-row alignment every softmax warp (32 tile rows
+// = 32 TMEM lanes) lies inside ONE group, so the score columns it needs are whole 32-column chunks
+// with compile-time masks (the dense packing of the previous version made every row read and
+// exponentiate up to 96 columns for 24 live keys, with run-time masks: 2-3 K instructions per unit).
+//
+// Per unit = (tile, head): S = Q K^T (128 x 128, three f16x3 passes into TMEM); softmax over the
+// row's own group; the un-normalised probabilities go back to tensor memory as fp16 hi/lo OVER the
+// scores (zeros outside the group; the A operand of the second MMA is read from TMEM); O = P V with V
+// as an MN-major shared-memory operand.  The off-diagonal blocks are wasted tensor math, which is cheap.
 //
 // Inputs are the per-head planes the qkv GEMM epilogue writes (EPI_PLANES): fp16 hi/lo arrays
 // [which(q,k,v) * 8 + head][token][hds], hds = head_dim rounded up to 16; the TMA box is HDP = 64 / 32
-// columns wide (one 128- / 64-byte swizzle span per tile row), columns past hds are zero-filled by
-// the TMA unit.
+// columns wide (one 128- / 64-byte swizzle span per tile row), columns past hds are zero-filled too.
 //
 //   warp 0     TMEM allocator, then TMA producer: one Q/K ring and one V ring, two stages each, so the
 //              next unit's Q,K are in flight while this unit's softmax and PV run
 //   warp 1     MMA issuer:   S = QK^T, O = PV, two units in flight (one per softmax group)
 //   warps 4-7  softmax group 0 (units 0, 2, 4, ... of this CTA), TMEM stage 0
-//   warps 8-11 softmax group 1 (units 1, 3, 5, ...), TMEM stage 1   (setmaxnreg: 232 registers each,
-//              taken from the control warpgroup, so a row's scores fit without spilling)
-//              thread = tile row = TMEM lane: the row's live score columns are read ONCE into registers
-//              (the first version read them twice and was TMEM-read / issue bound), masked max, exp2, sum,
-//              fp16 hi/lo -> TMEM, then O -> registers -> 1/sum -> fp16 hi/lo -> global [token, C]
+//   warps 8-11 softmax group 1 (units 1, 3, 5, ...), TMEM stage 1   (setmaxnreg: 216 registers each,
+//              taken from the control warpgroup)
+//              thread = tile row = TMEM lane: scores of the row's group read once into registers, max,
+//              exp2, sum, fp16 hi/lo -> TMEM; then O -> registers -> 1/sum -> fp16 hi/lo -> per-warp staging
+//              rows in shared memory -> 16-byte global stores of whole head slices of [token, C]
 #include "kernels.cuh"
 
 #include <cudaTypedefs.h>
@@ -36,20 +40,25 @@ namespace {
 
 constexpr int TILE_ROWS = 128;
 constexpr int ATT_THREADS = 384;
-constexpr int MAX_CH = 3;            // 32-column score chunks a softmax warp keeps in registers
 // TMEM columns: stage s holds S (fp32, 128 columns) at s*128, overwritten in place by P_hi (64 columns of
 // packed fp16 pairs) and P_lo (next 64); O (fp32, HDP columns) at 256 + s*64
 constexpr uint32_t TM_S = 0, TM_PLO = 64, TM_O = 256;
 
 struct AttnTcParams {
     int num_tiles;
-    int L, G;                 // group length and groups per tile (G*L <= 128)
+    int L, Lp, G;             // group length, padded length (multiple of 32), groups per tile (G*Lp <= 128)
     int hd, C;
     int temporal;
     int J, F;
     int tiles_per_seq;        // temporal: ceil(J / G)
+    int num_seqs;             // spatial: S*F sequences of L tokens
     long long M;              // valid token rows
     float scale_log2e;        // hd^-0.5 * log2(e)
+    int stg_pitch;            // output staging: bytes between rows (= 2*hd + 16)
+    int stg_warp_bytes;       // 32 staging rows, rounded up to 128 B
+    int chunk_bytes;          // 16, or 8 when a head slice is not 16-byte aligned in [token, C]
+    int chunks_per_row;       // 2*hd / chunk_bytes
+    int inv_cpr_q16;          // ceil(65536 / chunks_per_row)
     op_t* o_hi;
     op_t* o_lo;
 };
@@ -85,16 +94,16 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t r[1
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3, int32_t c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 
@@ -104,7 +113,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-// two probabilities in [0,1] -> packed fp16 hi pair and lo pair (no range clamp needed)
+// two values -> packed fp16 hi pair and lo pair.  No range clamp: probabilities are in [0,1], and the
+// attention output is a convex combination of V rows the GEMM epilogue already saturated to fp16 range.
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(a, b);
     const float2 hf = __half22float2(h);
@@ -113,7 +123,8 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-template <int HDP>
+// HDP: tile row width in fp16 elements (64 / 32).  LT: compile-time group length (0 = use p.L; NCH_MAX chunks)
+template <int HDP, int LT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                     const AttnTcParams p) {
@@ -122,6 +133,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     constexpr int STAGE_BYTES = 6 * TILE_BYTES;                // Qh Ql Kh Kl Vh Vl
     constexpr uint32_t LAYOUT = HDP == 64 ? 2u : 4u;
     constexpr uint32_t SBO = 8 * ROWB;
+    constexpr int NCH_MAX = LT ? (LT + 31) / 32 : 4;           // 32-column score chunks of one group
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t qk_full[2], qk_empty[2], v_full[2], v_empty[2];
     __shared__ __align__(8) uint64_t s_full[2], p_full[2], o_full[2], o_empty[2];
@@ -130,10 +142,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int L = LT ? LT : p.L;
+    const int Lp = LT ? NCH_MAX * 32 : p.Lp;
+    const int nch = LT ? NCH_MAX : p.Lp / 32;
     const int num_units = p.num_tiles * 8;
     const int n_local = (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int rows_used = p.G * p.L;                           // tile rows that hold tokens (= rows every TMA box writes)
-    const int key_steps = (rows_used + 15) / 16;               // 16-key MMA steps that can hold live keys
+    const int rows_box = p.G * Lp;                             // tile rows every TMA box writes (96 or 128)
+    const int key_steps = ((p.G - 1) * Lp + L + 15) / 16;      // 16-key MMA steps that can hold live keys
 
     // rows no box ever writes must not hold NaN bit patterns (0 * NaN in the PV product)
     for (int i = threadIdx.x; i < 2 * STAGE_BYTES / 16; i += ATT_THREADS)
@@ -169,25 +184,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t tile_tx = (uint32_t)(rows_used * ROWB);
+            const uint32_t tile_tx = (uint32_t)(rows_box * ROWB);          // zero-filled rows count too
             for (int it = 0; it < n_local; ++it) {
                 const int u = (int)blockIdx.x + it * (int)gridDim.x;
                 const int stage = it & 1;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 const int tile = u >> 3, head = u & 7;
                 uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-                int c1, c2;                                    // spatial: (row, -) ; temporal: (s*F, j0)
+                int ca, cb;                                    // spatial: (first sequence, -) ; temporal: (j0, s)
                 if (!p.temporal) {
-                    c1 = tile * rows_used;
-                    c2 = 0;
+                    ca = tile * p.G;
+                    cb = 0;
                 } else {
-                    c1 = (tile / p.tiles_per_seq) * p.F;
-                    c2 = (tile % p.tiles_per_seq) * p.G;
+                    ca = (tile % p.tiles_per_seq) * p.G;
+                    cb = tile / p.tiles_per_seq;
                 }
 #pragma unroll
                 for (int w = 0; w < 3; ++w) {                  // q, k, v
                     const int plane = w * 8 + head;
-                    uint64_t* bar;
                     if (w == 0) {
                         mbar_wait(&qk_empty[stage], ph ^ 1);   // QK^T of the unit that last used this stage has retired
                         mbar_arrive_expect_tx(&qk_full[stage], 4 * tile_tx);
@@ -195,13 +209,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                         mbar_wait(&v_empty[stage], ph ^ 1);    // PV of that unit has retired
                         mbar_arrive_expect_tx(&v_full[stage], 2 * tile_tx);
                     }
-                    bar = w == 2 ? &v_full[stage] : &qk_full[stage];
+                    uint64_t* bar = w == 2 ? &v_full[stage] : &qk_full[stage];
                     if (!p.temporal) {
-                        tma_load_3d(st + (2 * w) * TILE_BYTES, &tm_hi, bar, 0, c1, plane);
-                        tma_load_3d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, bar, 0, c1, plane);
+                        tma_load_4d(st + (2 * w) * TILE_BYTES, &tm_hi, bar, 0, 0, ca, plane);
+                        tma_load_4d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, bar, 0, 0, ca, plane);
                     } else {
-                        tma_load_4d(st + (2 * w) * TILE_BYTES, &tm_hi, bar, 0, c1, c2, plane);
-                        tma_load_4d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, bar, 0, c1, c2, plane);
+                        tma_load_5d(st + (2 * w) * TILE_BYTES, &tm_hi, bar, 0, 0, ca, cb, plane);
+                        tma_load_5d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, bar, 0, 0, ca, cb, plane);
                     }
                 }
             }
@@ -267,21 +281,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         const int wg = (warp - 4) >> 2;                        // softmax group = TMEM stage
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;                           // tile row == TMEM lane
-        const bool row_live = r < rows_used;
-        const int g = row_live ? r / p.L : 0;
-        const int klo = g * p.L;                               // this row's keys: [klo, klo + Leff)
-        const unsigned Leff = row_live ? (unsigned)p.L : 0u;
-        // keys any row of this warp can see (warp-uniform)
-        const int w_first = q * 32, w_last = min(q * 32 + 31, rows_used - 1);
-        const bool warp_live = w_first < rows_used;
-        const int wlo = warp_live ? (w_first / p.L) * p.L : 0;
-        const int whi = warp_live ? (w_last / p.L + 1) * p.L : 0;
-        const int c_base = wlo >> 5;
-        const int n_ch = warp_live ? ((whi + 31) >> 5) - c_base : 0;
+        // all 32 rows of a warp belong to one group (Lp is a multiple of 32)
+        const int g = (q * 32) / Lp;                           // group of this warp
+        const int row0_in_g = q * 32 - g * Lp;                 // first row of the warp inside its group
+        const bool warp_live = g < p.G && row0_in_g < L;       // the warp holds at least one token row
+        const int c0 = g * nch;                                // first 32-column score chunk of the group
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const uint32_t s_addr = tmem_base + lane_sel + TM_S + (uint32_t)wg * 128u;
         const uint32_t o_addr = tmem_base + lane_sel + TM_O + (uint32_t)wg * 64u;
         const float sc = p.scale_log2e;
+        uint8_t* stg = smem + 2 * STAGE_BYTES + (warp - 4) * p.stg_warp_bytes;   // this warp's output staging rows
+        uint8_t* my_row = stg + lane * p.stg_pitch;
+        const int n_zero_chunks = (key_steps + 1) / 2;         // 32-key chunks the PV product reads
         for (int it = wg; it < n_local; it += 2) {
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
             const int u = (int)blockIdx.x + it * (int)gridDim.x;
@@ -290,56 +301,53 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             tcgen05_fence_after();
             float sum = 0.f;
             if (warp_live) {
-                // ---- the live score columns of this row, once, into registers: at most MAX_CH 32-column
-                // chunks starting at chunk c_base hold keys any row of this warp may see (host-checked)
-                uint32_t sv[MAX_CH * 32];
+                // ---- the scores of this row against the keys of its group, once, into registers
+                uint32_t sv[NCH_MAX * 32];
 #pragma unroll
-                for (int k = 0; k < MAX_CH; ++k)
-                    if (k < n_ch) tmem_ld_32x32(s_addr + (uint32_t)((c_base + k) * 32), &sv[k * 32]);
+                for (int k = 0; k < NCH_MAX; ++k)
+                    if (k < nch) tmem_ld_32x32(s_addr + (uint32_t)((c0 + k) * 32), &sv[k * 32]);
                 tmem_ld_wait();
-                // ---- masked row maximum (other groups' keys -> -inf, kept in the registers)
-                float mx = -INFINITY;
+                // ---- row maximum over the L live keys (four chains)
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                for (int k = 0; k < MAX_CH; ++k)
-                    if (k < n_ch) {
-                        const int col0 = (c_base + k) * 32 - klo;
+                for (int k = 0; k < NCH_MAX; ++k)
+                    if (k < nch) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const bool mine = (unsigned)(col0 + i) < Leff;
-                            const float v = mine ? __uint_as_float(sv[k * 32 + i]) : -INFINITY;
-                            sv[k * 32 + i] = __float_as_uint(v);
-                            mx = fmaxf(mx, v);
-                        }
+                        for (int i = 0; i < 32; ++i)
+                            if (k * 32 + i < L) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[k * 32 + i]));
                     }
-                const float moff = row_live ? mx * sc : 0.f;
-                // ---- p = exp2(s*c - m*c), row sum, fp16 hi/lo over the scores (zeros outside the group)
+                const float moff = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
+                // ---- p = exp2(s*c - m*c), row sum, fp16 hi/lo over the scores
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int k = 0; k < MAX_CH; ++k)
-                    if (k < n_ch) {
+                for (int k = 0; k < NCH_MAX; ++k)
+                    if (k < nch) {
                         uint32_t hi16[16], lo16[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[k * 32 + 2 * i]), sc, -moff));
-                            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[k * 32 + 2 * i + 1]), sc, -moff));
-                            sum += p0 + p1;
+                            float p0 = 0.f, p1 = 0.f;
+                            if (k * 32 + 2 * i < L) p0 = fast_exp2(fmaf(__uint_as_float(sv[k * 32 + 2 * i]), sc, -moff));
+                            if (k * 32 + 2 * i + 1 < L) p1 = fast_exp2(fmaf(__uint_as_float(sv[k * 32 + 2 * i + 1]), sc, -moff));
+                            s4[i & 3] += p0 + p1;
                             split_pair(p0, p1, hi16[i], lo16[i]);
                         }
-                        tmem_st_32x16(s_addr + (uint32_t)((c_base + k) * 16), hi16);
-                        tmem_st_32x16(s_addr + TM_PLO + (uint32_t)((c_base + k) * 16), lo16);
+                        tmem_st_32x16(s_addr + (uint32_t)((c0 + k) * 16), hi16);
+                        tmem_st_32x16(s_addr + TM_PLO + (uint32_t)((c0 + k) * 16), lo16);
                     }
+                sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
                 {
                     uint32_t z[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) z[i] = 0u;
-                    for (int c = 0; 2 * c < key_steps; ++c)    // chunks the PV product reads but this warp never sees
-                        if (c < c_base || c >= c_base + n_ch) {
+                    for (int c = 0; c < n_zero_chunks; ++c)    // keys of the other groups: exact zeros
+                        if (c < c0 || c >= c0 + nch) {
                             tmem_st_32x16(s_addr + (uint32_t)(c * 16), z);
                             tmem_st_32x16(s_addr + TM_PLO + (uint32_t)(c * 16), z);
                         }
                 }
                 tmem_st_wait();
             }
-            // rows of a dead warp feed garbage into rows of O nobody stores: nothing to write for them
+            // rows of a dead warp feed stale bits into rows of O nobody stores: nothing to write for them
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[wg]);
@@ -355,32 +363,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_empty[wg]);
-            long long token = -1;
-            if (row_live) {
-                if (!p.temporal) {
-                    token = (long long)tile * rows_used + r;
-                } else {
-                    const int s = tile / p.tiles_per_seq;
-                    const int j = (tile % p.tiles_per_seq) * p.G + g;
-                    const int f = r - g * p.L;
-                    token = j < p.J ? ((long long)s * p.F + f) * p.J + j : -1;
-                }
-                if (token >= p.M) token = -1;
+            if (!warp_live) continue;
+            // token of staging row i of this warp = tok0 + i * tstride, for i < n_rows (all warp-uniform)
+            long long tok0;
+            int tstride, n_rows = min(32, L - row0_in_g);
+            if (!p.temporal) {
+                const int seq = tile * p.G + g;
+                tok0 = (long long)seq * L + row0_in_g;
+                tstride = 1;
+                if (seq >= p.num_seqs) n_rows = 0;
+            } else {
+                const int s = tile / p.tiles_per_seq;
+                const int j = (tile % p.tiles_per_seq) * p.G + g;
+                tok0 = ((long long)s * p.F + row0_in_g) * p.J + j;
+                tstride = p.J;
+                if (j >= p.J) n_rows = 0;
             }
-            if (token >= 0) {
-                const float inv = 1.0f / sum;
-                uint2* oh = reinterpret_cast<uint2*>(p.o_hi + (size_t)token * p.C + head * p.hd);
-                uint2* ol = reinterpret_cast<uint2*>(p.o_lo + (size_t)token * p.C + head * p.hd);
+            // O / sum -> fp16 hi/lo, once; each half goes through this warp's staging rows (pitch = row bytes + 16,
+            // bank-conflict free) so that the global stores are runs of whole head slices (a lane-per-row store
+            // touched 32 different sectors per instruction and cost 25 % of the kernel)
+            const float inv = 1.0f / sum;
+            uint32_t oh[HDP / 2], ol[HDP / 2];
 #pragma unroll
-                for (int i = 0; i < HDP / 4; ++i) {
-                    if (4 * i < p.hd) {
-                        float v4[4] = {__uint_as_float(ov[4 * i + 0]) * inv, __uint_as_float(ov[4 * i + 1]) * inv,
-                                       __uint_as_float(ov[4 * i + 2]) * inv, __uint_as_float(ov[4 * i + 3]) * inv};
-                        uint2 h, l;
-                        split4(v4, h, l);
-                        oh[i] = h;
-                        ol[i] = l;
-                    }
+            for (int i = 0; i < HDP / 2; ++i)
+                split_pair(__uint_as_float(ov[2 * i]) * inv, __uint_as_float(ov[2 * i + 1]) * inv, oh[i], ol[i]);
+            const int n_chunks = n_rows * p.chunks_per_row;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                __syncwarp();                                  // the previous copy-out has read the staging rows
+#pragma unroll
+                for (int i = 0; i < HDP / 4; ++i)
+                    if (4 * i < p.hd)
+                        *reinterpret_cast<uint2*>(my_row + 8 * i) =
+                            half == 0 ? make_uint2(oh[2 * i], oh[2 * i + 1]) : make_uint2(ol[2 * i], ol[2 * i + 1]);
+                __syncwarp();
+                uint8_t* obase = reinterpret_cast<uint8_t*>((half == 0 ? p.o_hi : p.o_lo) + head * p.hd);
+                for (int k = lane; k < n_chunks; k += 32) {
+                    const int row = (k * p.inv_cpr_q16) >> 16;                 // k / chunks_per_row
+                    const int cc = k - row * p.chunks_per_row;
+                    const uint8_t* src = stg + row * p.stg_pitch + cc * p.chunk_bytes;
+                    uint8_t* dst = obase + (size_t)(tok0 + (long long)row * tstride) * (size_t)(p.C * 2) + cc * p.chunk_bytes;
+                    if (p.chunk_bytes == 16) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+                    else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
                 }
             }
         }
@@ -413,26 +437,28 @@ int att_init() {
     return 0;
 }
 
-// planes [24][rows_cap][hds] fp16; the box is hdp >= hds columns wide (columns past hds are zero-filled).
-// Spatial: (hds, rows_cap, 24), box (hdp, G*L, 1).
-// Temporal: (hds, S*F [stride J*hds], J [stride hds], 24), box (hdp, F, G, 1): the box lands in shared
-// memory joint-major, i.e. as G groups of F consecutive rows.
+// planes [24][rows_cap][hds] fp16; the box is hdp >= hds columns and Lp >= L rows per group (everything past
+// the tensor extents is zero-filled).
+// Spatial:  (hds, L [stride hds], S*F sequences [stride L*hds], 24), box (hdp, Lp, G, 1).
+// Temporal: (hds, F [stride J*hds], J [stride hds], S [stride F*J*hds], 24), box (hdp, Lp, G, 1, 1): the box lands
+// in shared memory joint-major, i.e. as G groups of Lp consecutive rows.
 int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int hds, int hdp, bool temporal, int J, int F,
-                   int G, int L) {
+                   int S, int G, int L, int Lp) {
     const CUtensorMapSwizzle sw = hdp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint64_t e = 2;                                            // bytes per element
     CUresult r;
     if (!temporal) {
-        cuuint64_t dims[3] = {(cuuint64_t)hds, (cuuint64_t)rows_cap, 24};
-        cuuint64_t strides[2] = {(cuuint64_t)hds * 2, (cuuint64_t)rows_cap * hds * 2};
-        cuuint32_t box[3] = {(cuuint32_t)hdp, (cuuint32_t)(G * L), 1};
-        r = g_enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<op_t*>(base), dims, strides, box, estr,
+        cuuint64_t dims[4] = {(cuuint64_t)hds, (cuuint64_t)L, (cuuint64_t)((long long)S * F), 24};
+        cuuint64_t strides[3] = {hds * e, (cuuint64_t)L * hds * e, (cuuint64_t)rows_cap * hds * e};
+        cuuint32_t box[4] = {(cuuint32_t)hdp, (cuuint32_t)Lp, (cuuint32_t)G, 1};
+        r = g_enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<op_t*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
-        cuuint64_t dims[4] = {(cuuint64_t)hds, (cuuint64_t)(rows_cap / J), (cuuint64_t)J, 24};
-        cuuint64_t strides[3] = {(cuuint64_t)J * hds * 2, (cuuint64_t)hds * 2, (cuuint64_t)rows_cap * hds * 2};
-        cuuint32_t box[4] = {(cuuint32_t)hdp, (cuuint32_t)F, (cuuint32_t)G, 1};
-        r = g_enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<op_t*>(base), dims, strides, box, estr,
+        cuuint64_t dims[5] = {(cuuint64_t)hds, (cuuint64_t)F, (cuuint64_t)J, (cuuint64_t)S, 24};
+        cuuint64_t strides[4] = {(cuuint64_t)J * hds * e, hds * e, (cuuint64_t)F * J * hds * e, (cuuint64_t)rows_cap * hds * e};
+        cuuint32_t box[5] = {(cuuint32_t)hdp, (cuuint32_t)Lp, (cuuint32_t)G, 1, 1};
+        r = g_enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<op_t*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) {
@@ -443,14 +469,18 @@ int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int h
     return 0;
 }
 
-template <int HDP>
+template <int HDP, int LT>
 int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, cudaStream_t st) {
-    constexpr int SMEM = 2 * 6 * TILE_ROWS * HDP * 2 + 1024;
-    auto kern = attention_tc_kernel<HDP>;
-    static bool configured = false;
-    if (!configured) {
+    const int SMEM = 2 * 6 * TILE_ROWS * HDP * 2 + 8 * p.stg_warp_bytes + 1024;
+    if (SMEM > 227 * 1024) {
+        set_last_error("attention_tc: head_dim %d needs %d bytes of shared memory", p.hd, SMEM);
+        return -1;
+    }
+    auto kern = attention_tc_kernel<HDP, LT>;
+    static int configured = 0;
+    if (configured < SMEM) {
         PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        configured = true;
+        configured = SMEM;
     }
     const long long units = (long long)p.num_tiles * 8;
     const int grid = (int)(units < g_sms ? units : g_sms);
@@ -461,51 +491,56 @@ int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& 
 
 }  // namespace
 
-// groups per 128-row tile
-static int groups_per_tile(int L, bool temporal) { return temporal ? 4 : 128 / L; }
-
 int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int F, int J, int C, int temporal,
                         cudaStream_t st) {
     if (S == 0) return 0;
     if (int rc = att_init()) return rc;
     const int hd = C / 8, hds = attn_head_store(hd), hdp = hds > 32 ? 64 : 32;
-    if (hd > 64 || hd % 4 != 0 || (temporal ? F : J) > 128 || (temporal && 4 * F > 128) || pl.hds != hds ||
-        (temporal && pl.rows_cap % J != 0)) {
-        set_last_error("attention_tc: unsupported shape J=%d F=%d C=%d temporal=%d (plane width %d)", J, F, C, temporal, pl.hds);
+    const int L = temporal ? F : J;
+    if (hd > 64 || hd % 4 != 0 || L > 128 || pl.hds != hds || pl.rows_cap != (long long)S * F * J) {
+        set_last_error("attention_tc: unsupported shape J=%d F=%d C=%d temporal=%d (plane width %d, rows %lld)", J, F, C,
+                       temporal, pl.hds, pl.rows_cap);
         return -1;
     }
     AttnTcParams p;
     p.temporal = temporal ? 1 : 0;
-    p.L = temporal ? F : J;
-    p.G = groups_per_tile(p.L, temporal != 0);
+    p.L = L;
+    p.Lp = (L + 31) / 32 * 32;
+    p.G = 128 / p.Lp;
     p.hd = hd;
     p.C = C;
     p.J = J;
     p.F = F;
     p.M = (long long)S * F * J;
+    p.num_seqs = S * F;
     if (temporal) {
         p.tiles_per_seq = (J + p.G - 1) / p.G;
         p.num_tiles = S * p.tiles_per_seq;
     } else {
         p.tiles_per_seq = 0;
-        const long long rows_per_tile = (long long)p.G * p.L;
-        p.num_tiles = (int)((p.M + rows_per_tile - 1) / rows_per_tile);
-    }
-    for (int w0 = 0; w0 < p.G * p.L; w0 += 32) {            // live key chunks per softmax warp
-        const int w1 = (w0 + 31 < p.G * p.L - 1) ? w0 + 31 : p.G * p.L - 1;
-        const int lo = (w0 / p.L) * p.L, hi = (w1 / p.L + 1) * p.L;
-        if ((hi + 31) / 32 - lo / 32 > MAX_CH) {
-            set_last_error("attention_tc: group length %d needs more than %d score chunks per warp", p.L, MAX_CH);
-            return -1;
-        }
+        p.num_tiles = (p.num_seqs + p.G - 1) / p.G;
     }
     p.scale_log2e = (float)(pow((double)hd, -0.5) * 1.4426950408889634);
     p.o_hi = o_hi;
     p.o_lo = o_lo;
+    p.stg_pitch = 2 * hd + 16;
+    p.stg_warp_bytes = (32 * p.stg_pitch + 127) / 128 * 128;
+    p.chunk_bytes = (2 * hd) % 16 == 0 ? 16 : 8;              // hd % 4 == 0, so a slice is at least 8-byte aligned
+    p.chunks_per_row = 2 * hd / p.chunk_bytes;
+    p.inv_cpr_q16 = (65536 + p.chunks_per_row - 1) / p.chunks_per_row;
     CUtensorMap mh, ml;
-    if (int rc = make_plane_map(&mh, pl.hi, pl.rows_cap, hds, hdp, temporal != 0, J, F, p.G, p.L)) return rc;
-    if (int rc = make_plane_map(&ml, pl.lo, pl.rows_cap, hds, hdp, temporal != 0, J, F, p.G, p.L)) return rc;
-    return hdp == 64 ? launch_tc<64>(mh, ml, p, st) : launch_tc<32>(mh, ml, p, st);
+    if (int rc = make_plane_map(&mh, pl.hi, pl.rows_cap, hds, hdp, temporal != 0, J, F, S, p.G, L, p.Lp)) return rc;
+    if (int rc = make_plane_map(&ml, pl.lo, pl.rows_cap, hds, hdp, temporal != 0, J, F, S, p.G, L, p.Lp)) return rc;
+    // the group lengths of the H3WB parts get compile-time masks; anything else runs the generic instance
+    if (hdp == 64) {
+        if (L == 24) return launch_tc<64, 24>(mh, ml, p, st);
+        if (L == 27) return launch_tc<64, 27>(mh, ml, p, st);
+        return launch_tc<64, 0>(mh, ml, p, st);
+    }
+    if (L == 68) return launch_tc<32, 68>(mh, ml, p, st);
+    if (L == 42) return launch_tc<32, 42>(mh, ml, p, st);
+    if (L == 27) return launch_tc<32, 27>(mh, ml, p, st);
+    return launch_tc<32, 0>(mh, ml, p, st);
 }
 
 // fp32 qkv [M,3C] -> head planes (unit tests; the production path gets the planes from the qkv GEMM epilogue)

@@ -150,75 +150,88 @@ int launch_embed(const EmbedParams& p, cudaStream_t st) {
 //     = the shared Spatial_norm / Temporal_norm after every block (mixste.py:243,257,269,273)
 //       and the Temporal_pos_embed add before TTE block 0 (:250).
 // Second stage (g1 != nullptr):         a  = LN(x; g1,b1,eps1) -> fp16 hi/lo     (norm1 / norm2 of the next GEMM)
-// One warp per row, row kept in registers (C <= 32*MAXV).
-template <int MAXV>
-__global__ void ln_chain_kernel(LnParams p) {
-    int warps_per_block = blockDim.x >> 5;
-    long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+// One warp per row, row kept in registers as NV float4 per lane (channels 4*lane + 128*i): 16-byte loads
+// and stores of x, 8-byte stores of the fp16 halves.
+template <int NV>
+__device__ __forceinline__ void ln_row_stats(const float4 (&v)[NV], int lane, int C, float& mean, float& rstd, float eps) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);   // lanes past C hold zeros
+    const float invC = 1.0f / (float)C;
+    mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if (4 * lane + 128 * i < C) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    rstd = 1.0f / sqrtf(warp_sum(q) * invC + eps);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) ln_chain_kernel(LnParams p) {
+    const int warps_per_block = blockDim.x >> 5;
+    const long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (m >= p.M) return;
-    int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const int C = p.C;
     float* xr = p.x + (size_t)m * C;
-    float v[MAXV];
+    float4 v[NV];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        int c = lane + 32 * i;
-        v[i] = c < C ? xr[c] : 0.f;
+    for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        v[i] = c < C ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float invC = 1.0f / (float)C;
     if (p.g0) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) s += v[i];
-        float mean = warp_sum(s) * invC;
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            int c = lane + 32 * i;
-            float d = c < C ? v[i] - mean : 0.f;
-            q += d * d;
-        }
-        float rstd = (1.0f / sqrtf(warp_sum(q) * invC + p.eps0));
+        float mean, rstd;
+        ln_row_stats<NV>(v, lane, C, mean, rstd, p.eps0);
         const float* addr = nullptr;
         if (p.add_f) {
-            int f = (int)((m / p.J) % p.F);
+            const int f = (int)((m / p.J) % p.F);
             addr = p.add_f + (size_t)f * C;
         }
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            int c = lane + 32 * i;
+        for (int i = 0; i < NV; ++i) {
+            const int c = 4 * lane + 128 * i;
             if (c < C) {
-                float y = (v[i] - mean) * rstd * p.g0[c] + p.b0[c];
-                if (addr) y += addr[c];
+                const float4 g = __ldg(reinterpret_cast<const float4*>(p.g0 + c));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.b0 + c));
+                float4 y;
+                y.x = (v[i].x - mean) * rstd * g.x + b.x;
+                y.y = (v[i].y - mean) * rstd * g.y + b.y;
+                y.z = (v[i].z - mean) * rstd * g.z + b.z;
+                y.w = (v[i].w - mean) * rstd * g.w + b.w;
+                if (addr) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(addr + c));
+                    y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w;
+                }
                 v[i] = y;
-                xr[c] = y;
+                *reinterpret_cast<float4*>(xr + c) = y;
             }
         }
     }
     if (p.g1) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) s += v[i];
-        float mean = warp_sum(s) * invC;
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            int c = lane + 32 * i;
-            float d = c < C ? v[i] - mean : 0.f;
-            q += d * d;
-        }
-        float rstd = (1.0f / sqrtf(warp_sum(q) * invC + p.eps1));
+        float mean, rstd;
+        ln_row_stats<NV>(v, lane, C, mean, rstd, p.eps1);
         op_t* oh = p.out_hi + (size_t)m * C;
         op_t* ol = p.out_lo + (size_t)m * C;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            int c = lane + 32 * i;
+        for (int i = 0; i < NV; ++i) {
+            const int c = 4 * lane + 128 * i;
             if (c < C) {
-                float y = (v[i] - mean) * rstd * p.g1[c] + p.b1[c];
-                op_t h, l;
-                split_op(y, h, l);
-                oh[c] = h;
-                ol[c] = l;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(p.g1 + c));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.b1 + c));
+                float y[4];
+                y[0] = (v[i].x - mean) * rstd * g.x + b.x;
+                y[1] = (v[i].y - mean) * rstd * g.y + b.y;
+                y[2] = (v[i].z - mean) * rstd * g.z + b.z;
+                y[3] = (v[i].w - mean) * rstd * g.w + b.w;
+                uint2 h, l;
+                split4(y, h, l);
+                *reinterpret_cast<uint2*>(oh + c) = h;
+                *reinterpret_cast<uint2*>(ol + c) = l;
             }
         }
     }
@@ -228,14 +241,14 @@ int launch_ln_chain(const LnParams& p, cudaStream_t st) {
     if (p.M == 0) return 0;
     const int wpb = 8;
     unsigned blocks = (unsigned)((p.M + wpb - 1) / wpb);
-    if (p.C <= 256)
-        ln_chain_kernel<8><<<blocks, wpb * 32, 0, st>>>(p);
-    else if (p.C <= 384)
-        ln_chain_kernel<12><<<blocks, wpb * 32, 0, st>>>(p);
-    else {
-        set_last_error("ln_chain: C=%d > 384 unsupported", p.C);
+    if (p.C % 4 != 0 || p.C > 384) {
+        set_last_error("ln_chain: C=%d unsupported (multiple of 4, <= 384)", p.C);
         return -1;
     }
+    if (p.C <= 256)
+        ln_chain_kernel<2><<<blocks, wpb * 32, 0, st>>>(p);
+    else
+        ln_chain_kernel<3><<<blocks, wpb * 32, 0, st>>>(p);
     PAFUSE_LAUNCH_OK();
     return 0;
 }

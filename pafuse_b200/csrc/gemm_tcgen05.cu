@@ -17,11 +17,13 @@
 //   warp 0    TMA producer: 4 tiled loads per stage (A_hi, A_lo, W_hi, W_lo; 128B swizzle)
 //   warp 1    MMA issuer (even CTA only): 3 x (BK/16) tcgen05.mma per stage, commits to mbarriers
 //   warp 2    TMEM allocator (512 columns = two BN<=256 accumulator buffers)
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns, bias / GELU+split, swizzled st.shared into a
-//             per-warp staging box, TMA store of the 32x32 box (cp.reduce.async.bulk .add for the
-//             residual update x += y, performed at the L2).  The first version stored straight from
-//             registers, one row per lane: 32 different 128-byte lines per store instruction made the
-//             epilogue, not the tensor pipe, the critical path (profiles/r1_gemm_1cta.txt).
+//   warps 4-11 epilogue, two warps per TMEM lane quarter (even / odd 32-column chunks): tcgen05.ld 32 lanes
+//             x 32 columns, bias / GELU+split, swizzled st.shared into a per-warp staging box, TMA store of
+//             the box (cp.reduce.async.bulk .add for the residual update x += y, performed at the L2).
+//             The first version stored straight from registers, one row per lane: 32 different 128-byte
+//             lines per store instruction made the epilogue the critical path (profiles/r1a_*); the second
+//             had 4 epilogue warps and the GELU / head-plane epilogues (40 instructions per element at
+//             0.4 IPC) were still slower than the main loop (profiles/r1b_gemm_attention_ncu_full.txt).
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue),
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "kernels.cuh"
@@ -40,11 +42,12 @@ constexpr int UK = 16;               // K per tcgen05.mma (16-bit operands)
 constexpr int MAX_STAGES = 6;
 constexpr int A_TILE_BYTES = BM * BK * 2;           // 16 KiB
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
-constexpr int STG_WARP_BYTES = 8192;                // per epilogue warp: 2 staging buffers of 32 rows x 128 B
-constexpr int STG_BYTES = 4 * STG_WARP_BYTES;
+constexpr int STG_WARP_BYTES = 4096;                // per epilogue warp: one staging box of 32 rows x 128 B
+constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 
 struct KernelParams {
     long long M;
@@ -102,7 +105,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);                  // one tcgen05.commit
-            mbar_init(&tmem_empty_bar[a], 4 * CG);            // one elected lane per epilogue warp of every CTA of the group
+            mbar_init(&tmem_empty_bar[a], EPI_WARPS * CG);    // one elected lane per epilogue warp of every CTA of the group
         }
         fence_barrier_init();
     }
@@ -192,12 +195,12 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue (every CTA drains its own 128 accumulator rows) =====================
-        const int q = warp - EPI_WARP0;                               // TMEM lane quarter == warp % 4
+        const int q = warp & 3;                                       // TMEM lane quarter == warp % 4
+        const int half = (warp - EPI_WARP0) >> 2;                     // 0: even 32-column chunks, 1: odd
         int acc = 0;
         uint32_t acc_phase = 0;
         const float oscale = p.out_scale;
-        uint8_t* stg = smem + (size_t)p.stages * p.stage_bytes + q * STG_WARP_BYTES;   // 1024-byte aligned
-        int sbuf = 0;
+        uint8_t* box = smem + (size_t)p.stages * p.stage_bytes + (warp - EPI_WARP0) * STG_WARP_BYTES;   // 1024-byte aligned
         for (int tile = group; tile < num_tiles; tile += num_groups) {
             const int m_tile = tile / p.n_tiles;
             const int n_tile = tile % p.n_tiles;
@@ -205,21 +208,28 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             tcgen05_fence_after();
             const int row0 = (m_tile * CG + (int)cta_rank) * BM + q * 32;   // first row of this warp's box
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (half * 32 >= BN) {                                    // a 32-column tile has no odd chunk: nothing to read
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 1) mbar_arrive(&tmem_empty_bar[acc]);
+                    else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+                }
+            }
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 uint32_t r[32];
                 tmem_ld_32x32(t_base + (uint32_t)c0, r);
+                if (lane == 0) bulk_wait_group_read<0>();             // the store that last used the box has read it
                 tmem_ld_wait();
-                if (c0 + 32 >= BN) {                                  // accumulator fully read: hand the buffer back early
+                if (c0 + 64 >= BN) {                                  // this warp's share of the accumulator is read
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) {                                  // 4*CG arrivals release the buffer to the issuer
+                    if (lane == 0) {                                  // 8*CG arrivals release the buffer to the issuer
                         if (CG == 1) mbar_arrive(&tmem_empty_bar[acc]);
                         else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
                     }
                 }
                 const int col = n_tile * BN + c0;
-                uint8_t* box = stg + sbuf * (STG_WARP_BYTES / 2);
-                if (lane == 0) bulk_wait_group_read<1>();             // the store that last used this buffer has read it
                 __syncwarp();
                 const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
                 if (EPI == EPI_F32 || EPI == EPI_RESID) {
@@ -246,7 +256,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     // fp16 hi/lo outputs.  Wide boxes (GELU_SPLIT, PLANES with 32-column heads): two boxes of
                     // 32 rows x 64 B (hi, lo), 64-byte swizzle: chunk i of row r at i ^ ((r >> 1) & 3).
                     // Narrow boxes (PLANES with 48-column heads): per 16-column piece p one box of 32 rows x 32 B,
-                    // unswizzled, hi at p * 1024 and lo at 2048 + p * 1024.
+                    // 32-byte swizzle (chunk i of row r at i ^ ((r >> 2) & 1)), hi at p * 1024 and lo at 2048 + p * 1024.
                     const bool narrow = EPI == EPI_PLANES && p.plane_pw == 16;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -267,7 +277,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         uint2 h0, l0, h1, l1;
                         split4(v, h0, l0);
                         split4(v + 4, h1, l1);
-                        const int off = narrow ? (i >> 1) * 1024 + lane * 32 + (i & 1) * 16
+                        const int off = narrow ? (i >> 1) * 1024 + lane * 32 + (((i & 1) ^ ((lane >> 2) & 1)) << 4)
                                                : lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);
                         *reinterpret_cast<uint4*>(box + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
                         *reinterpret_cast<uint4*>(box + 2048 + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
@@ -292,7 +302,6 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         bulk_commit_group();
                     }
                 }
-                sbuf ^= 1;
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -351,7 +360,7 @@ int make_map_planes(CUtensorMap* map, const void* ptr, long long rows_cap, int h
     cuuint32_t box[3] = {(cuuint32_t)pw, 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, pw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, pw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled(planes) failed (%d) rows_cap=%lld hds=%d ptr=%p", (int)r, rows_cap, hds, ptr);

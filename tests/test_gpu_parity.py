@@ -79,7 +79,7 @@ def test_linear_ragged_rows(M):
     assert (out.double() - ref).abs().max().item() < 5e-5
 
 
-@pytest.mark.parametrize("J,C", [(24, 384), (68, 224), (42, 256)])
+@pytest.mark.parametrize("J,C", [(24, 384), (68, 224), (42, 256), (17, 256), (30, 384), (5, 224)])
 @pytest.mark.parametrize("temporal", [False, True])
 def test_attention(J, C, temporal):
     torch.manual_seed(J + C)

@@ -1,0 +1,54 @@
+"""Per-kernel, per-part summary of an ncu --csv launch list (time, DRAM bytes, tensor-pipe %).
+
+    python tools/ncu_by_part.py gpurun_out/x_launches.csv
+"""
+import collections
+import csv
+import re
+import sys
+
+
+def short(n):
+    return re.sub(r'\(.*', '', n).replace('void ', '').replace('pafuse::', '').replace('<unnamed>::', '')
+
+
+def main(path):
+    rows = list(csv.reader(l for l in open(path) if not l.startswith('==')))
+    hdr = rows[0]
+    ik, im, iv, iid, iu = (hdr.index(k) for k in ('Kernel Name', 'Metric Name', 'Metric Value', 'ID', 'Metric Unit'))
+    L = collections.OrderedDict()
+    for r in rows[1:]:
+        if len(r) <= iv:
+            continue
+        d = L.setdefault(r[iid], {'k': short(r[ik])})
+        try:
+            v = float(r[iv].replace(',', ''))
+        except ValueError:
+            v = 0.0
+        u = r[iu]
+        scale = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1.0)
+        d[r[im]] = v * scale
+    part = -1
+    names = ['body', 'face', 'hands']
+    agg = collections.OrderedDict()
+    for d in L.values():
+        if d['k'].startswith('embed'):
+            part += 1
+        a = agg.setdefault((part, d['k']), [0, 0.0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += d.get('gpu__time_duration.sum', 0.0)
+        a[2] += d.get('dram__bytes_read.sum', 0.0)
+        a[3] += d.get('dram__bytes_write.sum', 0.0)
+        a[4] += d.get('sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 0.0)
+    tot = sum(a[1] for a in agg.values())
+    print(f"# {path}: {len(L)} launches, {tot / 1e3:.2f} ms summed (cold-cache, serialised under ncu)")
+    print(f"{'part':6s}{'kernel':40s}{'n':>4s}{'avg us':>9s}{'share':>7s}{'rd MB':>9s}{'wr MB':>9s}{'DRAM GB/s':>10s}{'tensor %':>9s}")
+    for (p, n), a in agg.items():
+        nm = names[p % 3] if p >= 0 else '-'
+        us = a[1] / a[0]
+        print(f"{nm:6s}{n:40s}{a[0]:4d}{us:9.1f}{100 * a[1] / tot:6.1f}%{a[2] / a[0] / 1e6:9.1f}{a[3] / a[0] / 1e6:9.1f}"
+              f"{(a[2] + a[3]) / a[1] / 1e3:10.0f}{a[4] / a[0]:9.1f}")
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])
