@@ -147,6 +147,8 @@ int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable);
 int pafuse_set_debug_simt_attention(pafuse_ctx* ctx, int32_t enable);
 /* process-wide: 2 (default) = tcgen05 CTA pairs (cta_group::2, 256-row tiles), 1 = lone CTAs */
 int pafuse_set_gemm_cta_group(int32_t cta_group);
+/* process-wide: 1 (default) = weight-stationary GEMM tiles where the W slice fits in shared memory, 0 = always stream W */
+int pafuse_set_gemm_weight_stationary(int32_t enable);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,7 @@ _SIGNATURES = {
                                        c_void_p]),
     "pafuse_set_debug_simt_gemm": (c_int32, [c_void_p, c_int32]),
     "pafuse_set_gemm_cta_group": (c_int32, [c_int32]),
+    "pafuse_set_gemm_weight_stationary": (c_int32, [c_int32]),
     "pafuse_set_debug_simt_attention": (c_int32, [c_void_p, c_int32]),
 }
 
@@ -272,6 +273,10 @@ class NativeContext:
     def set_gemm_cta_group(self, cta_group: int):
         with torch.cuda.device(self.device):
             check(self.lib.pafuse_set_gemm_cta_group(int(cta_group)), "pafuse_set_gemm_cta_group")
+
+    def set_gemm_weight_stationary(self, enable: bool):
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_set_gemm_weight_stationary(1 if enable else 0), "pafuse_set_gemm_weight_stationary")
 
     def launch_count(self) -> int:
         return int(self.lib.pafuse_launch_count())

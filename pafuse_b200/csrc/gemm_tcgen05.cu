@@ -37,11 +37,11 @@ namespace pafuse {
 namespace {
 
 constexpr int BM = 128;              // rows per CTA = TMEM lanes
-constexpr int BK = 64;               // K slice per stage = one 128-byte swizzle span of fp16
+constexpr int BKW = 64;              // K extent of a W box = one 128-byte swizzle span of fp16
 constexpr int UK = 16;               // K per tcgen05.mma (16-bit operands)
-constexpr int MAX_STAGES = 6;
-constexpr int A_TILE_BYTES = BM * BK * 2;           // 16 KiB
+constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int SMEM_SLACK = 1024 + 512;              // alignment of the dynamic window + the static barriers
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 8;
@@ -56,13 +56,51 @@ struct KernelParams {
     int m_tiles, n_tiles;            // tiles of (BM*CG) x block_n
     int stages;
     int stage_bytes;                 // per CTA
+    int a_bk;                        // K extent of an A stage: 64 (128-byte swizzle) or 32 (64-byte swizzle)
+    int w_res_bytes;                 // weight-stationary mode: bytes of the resident W slice per CTA
+    int slots;                       // weight-stationary mode: groups of n_tiles CTA pairs
     float out_scale;                 // undoes WEIGHT_SCALE
     const float* bias;
     int hds;                         // EPI_PLANES: stored head width (columns per plane)
     int plane_pw;                    // EPI_PLANES: columns per output box, 32 (hds % 32 == 0) or 16
 };
 
-template <int EPI, int CG>
+// Tile walk of one CTA group.  Streaming mode: tiles (m, n) in m-major order, strided over the groups, so
+// consecutive groups share an A tile through the L2.  Weight-stationary mode (WRES): the group keeps one n tile
+// for the whole launch (its W slice stays in shared memory) and walks m tiles; the n_tiles groups of a "slot"
+// walk the same m tiles at the same time, so every A tile still comes from DRAM once.
+template <bool WRES>
+struct TileWalk {
+    int first, step, count, n_fixed, n_tiles;
+    __device__ TileWalk(const KernelParams& p, int group, int num_groups) {
+        n_tiles = p.n_tiles;
+        if (WRES) {
+            const int slot = group / p.n_tiles;
+            n_fixed = group % p.n_tiles;
+            first = slot;
+            step = p.slots;
+            count = slot < p.slots ? (p.m_tiles - slot + p.slots - 1) / p.slots : 0;
+        } else {
+            const int total = p.m_tiles * p.n_tiles;
+            n_fixed = 0;
+            first = group;
+            step = num_groups;
+            count = group < total ? (total - group + num_groups - 1) / num_groups : 0;
+        }
+    }
+    __device__ void at(int i, int& m_tile, int& n_tile) const {
+        const int t = first + i * step;
+        if (WRES) {
+            m_tile = t;
+            n_tile = n_fixed;
+        } else {
+            m_tile = t / n_tiles;
+            n_tile = t % n_tiles;
+        }
+    }
+};
+
+template <int EPI, int CG, bool WRES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -73,22 +111,26 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t w_full_bar;
     __shared__ uint32_t tmem_base_slot;
 
-    // operand stages must sit on 1024-byte boundaries for the 128B swizzle atoms
+    // operand tiles must sit on 1024-byte boundaries for the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_w = smem;                                   // WRES: [K/64][hi, lo][WN rows x 128 B]
+    uint8_t* smem_st = smem + (WRES ? p.w_res_bytes : 0);     // operand stage ring
+    uint8_t* smem_box = smem_st + (size_t)p.stages * p.stage_bytes;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     const int BN = p.block_n;
-    const int WN = BN / CG;                                   // W rows this CTA loads per stage
-    const int w_tile_bytes = WN * BK * 2;
-    const int num_kb = (p.K + BK - 1) / BK;
-    const int num_tiles = p.m_tiles * p.n_tiles;
-    const int group = blockIdx.x / CG;                        // CTA pair (or CTA) index
-    const int num_groups = gridDim.x / CG;
+    const int WN = BN / CG;                                   // W rows this CTA loads
+    const int w_box_bytes = WN * BKW * 2;
+    const int a_bk = WRES ? p.a_bk : BKW;
+    const int a_tile_bytes = BM * a_bk * 2;
+    const int num_kb = (p.K + a_bk - 1) / a_bk;
+    const TileWalk<WRES> walk(p, (int)blockIdx.x / CG, (int)gridDim.x / CG);
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tm_a_hi);
@@ -107,6 +149,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             mbar_init(&tmem_full_bar[a], 1);                  // one tcgen05.commit
             mbar_init(&tmem_empty_bar[a], EPI_WARPS * CG);    // one elected lane per epilogue warp of every CTA of the group
         }
+        mbar_init(&w_full_bar, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -120,30 +163,51 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA loads its own operands) =====================
-        if (lane == 0) {
+        if (lane == 0 && walk.count > 0) {
+            if (WRES) {
+                // the whole K extent of this group's W slice, once
+                const int n0 = walk.n_fixed * BN + (int)cta_rank * WN;
+                const int nkw = (p.K + BKW - 1) / BKW;
+                if (CG == 1) mbar_arrive_expect_tx(&w_full_bar, (uint32_t)p.w_res_bytes);
+                else if (leader) mbar_arrive_expect_tx(&w_full_bar, (uint32_t)(2 * p.w_res_bytes));
+                for (int kw = 0; kw < nkw; ++kw) {
+                    uint8_t* dst = smem_w + (size_t)kw * 2 * w_box_bytes;
+                    if (CG == 1) {
+                        tma_load_2d(dst, &tm_w_hi, &w_full_bar, kw * BKW, n0);
+                        tma_load_2d(dst + w_box_bytes, &tm_w_lo, &w_full_bar, kw * BKW, n0);
+                    } else {
+                        tma_load_2d_pair(dst, &tm_w_hi, &w_full_bar, kw * BKW, n0);
+                        tma_load_2d_pair(dst + w_box_bytes, &tm_w_lo, &w_full_bar, kw * BKW, n0);
+                    }
+                }
+            }
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = group; tile < num_tiles; tile += num_groups) {
-                const int m_tile = tile / p.n_tiles;
-                const int n_tile = tile % p.n_tiles;
+            for (int i = 0; i < walk.count; ++i) {
+                int m_tile, n_tile;
+                walk.at(i, m_tile, n_tile);
                 const int m0 = (m_tile * CG + (int)cta_rank) * BM;
                 const int n0 = n_tile * BN + (int)cta_rank * WN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);  // MMAs that read this stage (in both CTAs) have retired
-                    uint8_t* st = smem + (size_t)stage * p.stage_bytes;
+                    uint8_t* st = smem_st + (size_t)stage * p.stage_bytes;
                     if (CG == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
-                        tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
-                        tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m0);
-                        tma_load_2d(st + 2 * A_TILE_BYTES, &tm_w_hi, &full_bar[stage], kb * BK, n0);
-                        tma_load_2d(st + 2 * A_TILE_BYTES + w_tile_bytes, &tm_w_lo, &full_bar[stage], kb * BK, n0);
+                        tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * a_bk, m0);
+                        tma_load_2d(st + a_tile_bytes, &tm_a_lo, &full_bar[stage], kb * a_bk, m0);
+                        if (!WRES) {
+                            tma_load_2d(st + 2 * a_tile_bytes, &tm_w_hi, &full_bar[stage], kb * BKW, n0);
+                            tma_load_2d(st + 2 * a_tile_bytes + w_box_bytes, &tm_w_lo, &full_bar[stage], kb * BKW, n0);
+                        }
                     } else {
                         // both CTAs' bytes are counted on the leader's barrier
                         if (leader) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 * p.stage_bytes));
-                        tma_load_2d_pair(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
-                        tma_load_2d_pair(st + A_TILE_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m0);
-                        tma_load_2d_pair(st + 2 * A_TILE_BYTES, &tm_w_hi, &full_bar[stage], kb * BK, n0);
-                        tma_load_2d_pair(st + 2 * A_TILE_BYTES + w_tile_bytes, &tm_w_lo, &full_bar[stage], kb * BK, n0);
+                        tma_load_2d_pair(st, &tm_a_hi, &full_bar[stage], kb * a_bk, m0);
+                        tma_load_2d_pair(st + a_tile_bytes, &tm_a_lo, &full_bar[stage], kb * a_bk, m0);
+                        if (!WRES) {
+                            tma_load_2d_pair(st + 2 * a_tile_bytes, &tm_w_hi, &full_bar[stage], kb * BKW, n0);
+                            tma_load_2d_pair(st + 2 * a_tile_bytes + w_box_bytes, &tm_w_lo, &full_bar[stage], kb * BKW, n0);
+                        }
                     }
                     if (++stage == p.stages) {
                         stage = 0;
@@ -154,28 +218,42 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread of the group's even CTA) =====================
-        if (lane == 0 && leader) {
+        if (lane == 0 && leader && walk.count > 0) {
             const uint32_t idesc = make_idesc_f16((uint32_t)(BM * CG), (uint32_t)BN);
+            const uint32_t a_layout = a_bk == 64 ? 2u : 4u;           // 128-byte / 64-byte swizzle
+            const uint32_t a_sbo = 8u * (uint32_t)a_bk * 2u;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = group; tile < num_tiles; tile += num_groups) {
+            if (WRES) {
+                mbar_wait(&w_full_bar, 0);                            // the resident W slice landed (in both CTAs)
+                tcgen05_fence_after();
+            }
+            for (int i = 0; i < walk.count; ++i) {
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // every epilogue warp of the group drained this buffer
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);               // operands landed (in both CTAs)
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-                    const uint32_t a_hi = sa, a_lo = sa + A_TILE_BYTES;
-                    const uint32_t w_hi = sa + 2 * A_TILE_BYTES, w_lo = w_hi + w_tile_bytes;
-                    int k_left = p.K - kb * BK;
-                    int nk = k_left >= BK ? BK / UK : (k_left + UK - 1) / UK;   // K tail: TMA zero-fills, skip dead slices
+                    const uint32_t sa = smem_u32(smem_st + (size_t)stage * p.stage_bytes);
+                    const uint32_t a_hi = sa, a_lo = sa + a_tile_bytes;
+                    uint32_t w_hi, w_lo;
+                    if (WRES) {
+                        const int k0 = kb * a_bk;                     // a_bk divides 64: the stage lies inside one W box
+                        w_hi = smem_u32(smem_w) + (uint32_t)(k0 / BKW) * 2u * (uint32_t)w_box_bytes + (uint32_t)(k0 % BKW) * 2u;
+                        w_lo = w_hi + w_box_bytes;
+                    } else {
+                        w_hi = sa + 2 * a_tile_bytes;
+                        w_lo = w_hi + w_box_bytes;
+                    }
+                    int k_left = p.K - kb * a_bk;
+                    int nk = k_left >= a_bk ? a_bk / UK : (k_left + UK - 1) / UK;   // K tail: TMA zero-fills, skip dead slices
                     for (int k = 0; k < nk; ++k) {
                         const uint32_t koff = (uint32_t)k * UK * 2;   // bytes along K inside the swizzle span
-                        const uint64_t dah = make_smem_desc_sw128(a_hi + koff);
-                        const uint64_t dal = make_smem_desc_sw128(a_lo + koff);
+                        const uint64_t dah = make_smem_desc(a_hi + koff, a_sbo, a_layout);
+                        const uint64_t dal = make_smem_desc(a_lo + koff, a_sbo, a_layout);
                         const uint64_t dwh = make_smem_desc_sw128(w_hi + koff);
                         const uint64_t dwl = make_smem_desc_sw128(w_lo + koff);
                         umma_f16_ss<CG>(d_tmem, dal, dwh, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
@@ -200,10 +278,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         int acc = 0;
         uint32_t acc_phase = 0;
         const float oscale = p.out_scale;
-        uint8_t* box = smem + (size_t)p.stages * p.stage_bytes + (warp - EPI_WARP0) * STG_WARP_BYTES;   // 1024-byte aligned
-        for (int tile = group; tile < num_tiles; tile += num_groups) {
-            const int m_tile = tile / p.n_tiles;
-            const int n_tile = tile % p.n_tiles;
+        uint8_t* box = smem_box + (warp - EPI_WARP0) * STG_WARP_BYTES;   // 1024-byte aligned
+        for (int it = 0; it < walk.count; ++it) {
+            int m_tile, n_tile;
+            walk.at(it, m_tile, n_tile);
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
             const int row0 = (m_tile * CG + (int)cta_rank) * BM + q * 32;   // first row of this warp's box
@@ -272,11 +350,13 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         v[7] = fmaf(__uint_as_float(r[8 * i + 7]), oscale, b1.w);
                         if (EPI == EPI_GELU_SPLIT) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+                            for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
                         }
                         uint2 h0, l0, h1, l1;
-                        split4(v, h0, l0);
-                        split4(v + 4, h1, l1);
+                        split_pair_sat(v[0], v[1], h0.x, l0.x);
+                        split_pair_sat(v[2], v[3], h0.y, l0.y);
+                        split_pair_sat(v[4], v[5], h1.x, l1.x);
+                        split_pair_sat(v[6], v[7], h1.y, l1.y);
                         const int off = narrow ? (i >> 1) * 1024 + lane * 32 + (((i & 1) ^ ((lane >> 2) & 1)) << 4)
                                                : lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);
                         *reinterpret_cast<uint4*>(box + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
@@ -320,14 +400,15 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 // ------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
-int make_map_f16(CUtensorMap* map, const void* ptr, long long rows, int K, int box_rows) {
+// operand boxes: box_k (64 / 32) columns x box_rows rows, swizzle span = the bytes of one box row
+int make_map_f16(CUtensorMap* map, const void* ptr, long long rows, int K, int box_rows, int box_k = BKW) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%d box_rows=%d ptr=%p", (int)r, rows, K, box_rows,
                        ptr);
@@ -371,15 +452,17 @@ int make_map_planes(CUtensorMap* map, const void* ptr, long long rows_cap, int h
 
 int g_num_sms = 0;
 int g_force_cg = 0;      // PAFUSE_GEMM_CTA_GROUP=1|2 overrides the default (2)
+int g_wres_enabled = 1;  // PAFUSE_GEMM_WRES=0 disables the weight-stationary mode
+int g_wres_min_stages = 3;
 
-template <int EPI, int CG>
+template <int EPI, int CG, bool WRES>
 int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
                const CUtensorMap& o0, const CUtensorMap& o1, const KernelParams& kp, int grid, int smem,
                cudaStream_t st) {
-    auto kern = gemm_f16x3_kernel<EPI, CG>;
+    auto kern = gemm_f16x3_kernel<EPI, CG, WRES>;
     static bool configured = false;                                   // per template instance
     if (!configured) {
-        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024));
+        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 512));
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -399,6 +482,13 @@ int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
     return 0;
 }
 
+template <int EPI, int CG>
+int launch_mode(bool wres, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
+                const CUtensorMap& o0, const CUtensorMap& o1, const KernelParams& kp, int grid, int smem, cudaStream_t st) {
+    return wres ? launch_epi<EPI, CG, true>(ah, al, wh, wl, o0, o1, kp, grid, smem, st)
+                : launch_epi<EPI, CG, false>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
+}
+
 template <int CG>
 int launch_cg(const GemmArgs& g, cudaStream_t st) {
     const int BN = gemm_pick_block_n(g.N);
@@ -406,12 +496,6 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
         set_last_error("gemm: unsupported shape N=%d K=%d (block_n=%d)", g.N, g.K, BN);
         return -1;
     }
-    CUtensorMap ah, al, wh, wl;
-    if (int rc = make_map_f16(&ah, g.a_hi, g.M, g.K, BM)) return rc;
-    if (int rc = make_map_f16(&al, g.a_lo, g.M, g.K, BM)) return rc;
-    if (int rc = make_map_f16(&wh, g.w_hi, g.N, g.K, BN / CG)) return rc;
-    if (int rc = make_map_f16(&wl, g.w_lo, g.N, g.K, BN / CG)) return rc;
-
     KernelParams kp;
     kp.M = g.M;
     kp.N = g.N;
@@ -419,14 +503,45 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     kp.block_n = BN;
     kp.m_tiles = (int)((g.M + BM * CG - 1) / (BM * CG));
     kp.n_tiles = g.N / BN;
-    kp.stage_bytes = 2 * A_TILE_BYTES + 2 * (BN / CG) * BK * 2;
-    int stages = (SMEM_LIMIT - 2048 - 1024 - STG_BYTES) / kp.stage_bytes;   // 1 KiB alignment slack + static barriers
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    kp.stages = stages;
     kp.out_scale = g.out_scale;
     kp.bias = g.bias;
     kp.hds = g.planes.hds;
     kp.plane_pw = g.planes.hds % 32 == 0 ? 32 : 16;
+    const int max_groups = g_num_sms / CG;
+    const int WN = BN / CG;
+
+    // Weight-stationary mode: the W slice of one n tile (all of K, hi and lo) stays in shared memory and only A
+    // is streamed, in 32-wide K stages.  Chosen when the slice leaves room for >= 3 stages; the K = 2C layers
+    // (fc2) do not fit and stream both operands.
+    bool wres = false;
+    kp.a_bk = BKW;
+    kp.w_res_bytes = 0;
+    kp.slots = 0;
+    if (g_wres_enabled && g.K % 32 == 0 && kp.n_tiles <= max_groups) {
+        const int w_res = ((g.K + BKW - 1) / BKW) * 2 * WN * BKW * 2;
+        const int a_stage = 2 * BM * 32 * 2;
+        const int stages = (SMEM_LIMIT - SMEM_SLACK - STG_BYTES - w_res) / a_stage;
+        if (stages >= g_wres_min_stages) {
+            wres = true;
+            kp.a_bk = 32;
+            kp.w_res_bytes = w_res;
+            kp.stage_bytes = a_stage;
+            kp.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+            kp.slots = max_groups / kp.n_tiles;
+            if (kp.slots > kp.m_tiles) kp.slots = kp.m_tiles;
+        }
+    }
+    if (!wres) {
+        kp.stage_bytes = 2 * BM * BKW * 2 + 2 * WN * BKW * 2;
+        int stages = (SMEM_LIMIT - SMEM_SLACK - STG_BYTES) / kp.stage_bytes;
+        kp.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    }
+
+    CUtensorMap ah, al, wh, wl;
+    if (int rc = make_map_f16(&ah, g.a_hi, g.M, g.K, BM, kp.a_bk)) return rc;
+    if (int rc = make_map_f16(&al, g.a_lo, g.M, g.K, BM, kp.a_bk)) return rc;
+    if (int rc = make_map_f16(&wh, g.w_hi, g.N, g.K, WN)) return rc;
+    if (int rc = make_map_f16(&wl, g.w_lo, g.N, g.K, WN)) return rc;
     CUtensorMap o0, o1;
     if (g.epilogue == EPI_PLANES) {
         if (g.planes.hds < 16 || g.planes.hds % 16 != 0 || g.N != 24 * g.planes.hds || g.planes.rows_cap < g.M) {
@@ -442,15 +557,19 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
         if (int rc = make_map_out(&o0, g.out_f32, g.M, g.N, true)) return rc;
         o1 = o0;
     }
-    const int smem = stages * kp.stage_bytes + STG_BYTES + 1024;
-    const long long tiles = (long long)kp.m_tiles * kp.n_tiles;
-    const int max_groups = g_num_sms / CG;
-    const int grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;
+    const int smem = kp.w_res_bytes + kp.stages * kp.stage_bytes + STG_BYTES + 1024;
+    int grid;
+    if (wres) {
+        grid = kp.slots * kp.n_tiles * CG;
+    } else {
+        const long long tiles = (long long)kp.m_tiles * kp.n_tiles;
+        grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;
+    }
     switch (g.epilogue) {
-        case EPI_F32: return launch_epi<EPI_F32, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
-        case EPI_GELU_SPLIT: return launch_epi<EPI_GELU_SPLIT, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
-        case EPI_RESID: return launch_epi<EPI_RESID, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
-        case EPI_PLANES: return launch_epi<EPI_PLANES, CG>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
+        case EPI_F32: return launch_mode<EPI_F32, CG>(wres, ah, al, wh, wl, o0, o1, kp, grid, smem, st);
+        case EPI_GELU_SPLIT: return launch_mode<EPI_GELU_SPLIT, CG>(wres, ah, al, wh, wl, o0, o1, kp, grid, smem, st);
+        case EPI_RESID: return launch_mode<EPI_RESID, CG>(wres, ah, al, wh, wl, o0, o1, kp, grid, smem, st);
+        case EPI_PLANES: return launch_mode<EPI_PLANES, CG>(wres, ah, al, wh, wl, o0, o1, kp, grid, smem, st);
     }
     set_last_error("gemm: bad epilogue %d", g.epilogue);
     return -1;
@@ -481,10 +600,13 @@ int gemm_init() {
     PAFUSE_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     const char* e = getenv("PAFUSE_GEMM_CTA_GROUP");
     g_force_cg = e ? atoi(e) : 0;
+    if (const char* w = getenv("PAFUSE_GEMM_WRES")) g_wres_enabled = atoi(w);
+    if (const char* w = getenv("PAFUSE_GEMM_WRES_MIN_STAGES")) g_wres_min_stages = atoi(w);
     return 0;
 }
 
 void gemm_set_cta_group(int cg) { g_force_cg = cg; }
+void gemm_set_weight_stationary(int on) { g_wres_enabled = on; }
 
 int launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t st) {
     if (g.M == 0) return 0;

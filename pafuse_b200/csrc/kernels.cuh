@@ -138,5 +138,6 @@ int launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);   // debug reference (CUDA cores)
 int gemm_pick_block_n(int N);
 void gemm_set_cta_group(int cg);                            // 1: lone CTAs, 2 (default): tcgen05 CTA pairs
+void gemm_set_weight_stationary(int on);                    // 1 (default): keep the W slice of an n tile in shared memory when it fits
 
 }  // namespace pafuse

@@ -640,6 +640,12 @@ int pafuse_set_gemm_cta_group(int32_t cta_group) {
     return 0;
 }
 
+int pafuse_set_gemm_weight_stationary(int32_t enable) {
+    if (int rc = gemm_init()) return rc;
+    gemm_set_weight_stationary(enable != 0);
+    return 0;
+}
+
 int pafuse_profile_enable(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     Profiler& pr = ctx->prof;

@@ -79,6 +79,35 @@ def test_linear_ragged_rows(M):
     assert (out.double() - ref).abs().max().item() < 5e-5
 
 
+@pytest.mark.parametrize("N,K", [(1152, 384), (384, 384), (768, 384), (768, 224), (224, 224), (448, 224), (768, 256),
+                                 (256, 256), (512, 256), (32, 64)])
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_weight_stationary_tiles_equal_streamed_tiles(N, K, epi):
+    """Both GEMM schedules issue the same MMA sequence per output tile: results must be bit-identical."""
+    torch.manual_seed(N + K + epi)
+    c = _ctx()
+    M = 74 * 256 * 2 + 300                                            # several m tiles per CTA pair + a ragged one
+    x = torch.randn(M, K, device="cuda")
+    w = (torch.rand(N, K, device="cuda") * 2 - 1) / K ** 0.5
+    b = torch.randn(N, device="cuda") * 0.1
+    y0 = torch.randn(M, N, device="cuda")
+    try:
+        c.set_gemm_weight_stationary(False)
+        streamed = c.linear(x, w, b, epilogue=epi, y=y0.clone())
+        c.set_gemm_weight_stationary(True)
+        resident = c.linear(x, w, b, epilogue=epi, y=y0.clone())
+    finally:
+        c.set_gemm_weight_stationary(True)
+    torch.cuda.synchronize()
+    assert torch.equal(streamed, resident)      # epi 2: x += y is one L2-side add per element in both schedules
+    ref = x.double() @ w.double().t() + b.double()
+    if epi == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if epi == 2:
+        ref = ref + y0.double()
+    assert (resident.double() - ref).abs().max().item() < 5e-5
+
+
 @pytest.mark.parametrize("J,C", [(24, 384), (68, 224), (42, 256), (17, 256), (30, 384), (5, 224)])
 @pytest.mark.parametrize("temporal", [False, True])
 def test_attention(J, C, temporal):
