@@ -20,9 +20,9 @@
 // [which(q,k,v) * 8 + head][token][hds], hds = head_dim rounded up to 16; the TMA box is HDP = 64 / 32
 // columns wide (one 128- / 64-byte swizzle span per tile row), columns past hds are zero-filled too.
 //
-//   warp 0     TMEM allocator, then TMA producer: one Q/K ring and one V ring, two stages each, so the
-//              next unit's Q,K are in flight while this unit's softmax and PV run
-//   warp 1     MMA issuer:   S = QK^T, O = PV, two units in flight (one per softmax group)
+//   warps 0,3  TMA producers, one per ring stage (warp 0 also allocates the tensor memory): a Q/K ring and a V
+//              ring, two stages each, so the next unit's Q,K are in flight while this unit's softmax and PV run
+//   warps 1,2  MMA issuers, one per stage:   S = QK^T, O = PV, two units in flight (one per softmax group)
 //   warps 4-7  softmax group 0 (units 0, 2, 4, ... of this CTA), TMEM stage 0
 //   warps 8-11 softmax group 1 (units 1, 3, 5, ...), TMEM stage 1   (setmaxnreg: 216 registers each,
 //              taken from the control warpgroup)
@@ -181,16 +181,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");                   // control warpgroup donates registers ...
-    if (warp == 0) {
-        // ===================== TMA producer =====================
+    if (warp == 0 || warp == 3) {
+        // ===================== TMA producers: warp 0 feeds ring stage 0 (units 0, 2, ...), warp 3 stage 1 ==========
+        // (one thread for both stages made the Q,K loads of unit i+1 queue behind the wait for PV of unit i-2)
         if (lane == 0) {
+            const int stage = warp == 0 ? 0 : 1;
             const uint32_t tile_tx = (uint32_t)(rows_box * ROWB);          // zero-filled rows count too
-            for (int it = 0; it < n_local; ++it) {
+            uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+            for (int it = stage; it < n_local; it += 2) {
                 const int u = (int)blockIdx.x + it * (int)gridDim.x;
-                const int stage = it & 1;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 const int tile = u >> 3, head = u & 7;
-                uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
                 int ca, cb;                                    // spatial: (first sequence, -) ; temporal: (j0, s)
                 if (!p.temporal) {
                     ca = tile * p.G;
@@ -220,54 +221,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else {
+        // ===================== MMA issuers: warp 1 drives stage 0, warp 2 stage 1 =====================
+        // Per stage the order QK(i), PV(i), QK(i+2), PV(i+2), ... is what lets S alias P; the two stages are
+        // independent, and with one issuing thread PV(i+1) used to wait behind the operands of QK(i+2).
         if (lane == 0) {
+            const int stage = warp - 1;
             const uint32_t idesc_qk = make_idesc_f16(128, (uint32_t)(key_steps * 16));
             const uint32_t idesc_pv = make_idesc_f16(128, HDP) | (1u << 16);      // B (= V) is MN-major
+            const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+            const uint32_t d_s = tmem_base + TM_S + (uint32_t)stage * 128u;
+            const uint32_t d_o = tmem_base + TM_O + (uint32_t)stage * 64u;
             auto issue_qk = [&](int it) {
-                const int stage = it & 1;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(&qk_full[stage], ph);
                 tcgen05_fence_after();
-                // S[stage] aliases P[stage] of unit it-2: that PV was issued before this point and the
-                // tensor pipe executes in issue order
-                const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                const uint32_t d = tmem_base + TM_S + (uint32_t)stage * 128u;
+                // S[stage] aliases P[stage] of unit it-2: that PV was issued by this thread before this point and
+                // the tensor pipe executes in issue order
 #pragma unroll
                 for (int k = 0; k < HDP / 16; ++k) {
                     const uint32_t ko = (uint32_t)k * 32u;
                     const uint64_t qh = make_desc(sa + ko, SBO, LAYOUT), ql = make_desc(sa + TILE_BYTES + ko, SBO, LAYOUT);
                     const uint64_t kh = make_desc(sa + 2 * TILE_BYTES + ko, SBO, LAYOUT);
                     const uint64_t kl = make_desc(sa + 3 * TILE_BYTES + ko, SBO, LAYOUT);
-                    umma_f16_ss<1>(d, ql, kh, idesc_qk, k != 0 ? 1u : 0u);
-                    umma_f16_ss<1>(d, qh, kl, idesc_qk, 1u);
-                    umma_f16_ss<1>(d, qh, kh, idesc_qk, 1u);
+                    umma_f16_ss<1>(d_s, ql, kh, idesc_qk, k != 0 ? 1u : 0u);
+                    umma_f16_ss<1>(d_s, qh, kl, idesc_qk, 1u);
+                    umma_f16_ss<1>(d_s, qh, kh, idesc_qk, 1u);
                 }
                 umma_commit<1>(&qk_empty[stage]);              // Q,K tiles of this stage may be overwritten
                 umma_commit<1>(&s_full[stage]);
             };
-            if (n_local > 0) issue_qk(0);
-            if (n_local > 1) issue_qk(1);
-            for (int it = 0; it < n_local; ++it) {
-                const int stage = it & 1;
+            if (stage < n_local) issue_qk(stage);
+            for (int it = stage; it < n_local; it += 2) {
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(&v_full[stage], ph);
                 mbar_wait(&o_empty[stage], ph ^ 1);            // the softmax group has read O of unit it-2
                 mbar_wait(&p_full[stage], ph);                 // P of this unit is in tensor memory
                 tcgen05_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                const uint32_t d = tmem_base + TM_O + (uint32_t)stage * 64u;
-                const uint32_t pbase = tmem_base + TM_S + (uint32_t)stage * 128u;
                 for (int k = 0; k < key_steps; ++k) {
                     const uint32_t vo = (uint32_t)k * 16u * ROWB;                 // 16 keys further down the V tile
                     const uint64_t vh = make_desc(sa + 4 * TILE_BYTES + vo, SBO, LAYOUT);
                     const uint64_t vl = make_desc(sa + 5 * TILE_BYTES + vo, SBO, LAYOUT);
-                    const uint32_t ph_a = pbase + (uint32_t)k * 8u;               // 16 fp16 keys = 8 columns
-                    const uint32_t pl_a = pbase + TM_PLO + (uint32_t)k * 8u;
-                    umma_f16_ts(d, pl_a, vh, idesc_pv, k != 0 ? 1u : 0u);
-                    umma_f16_ts(d, ph_a, vl, idesc_pv, 1u);
-                    umma_f16_ts(d, ph_a, vh, idesc_pv, 1u);
+                    const uint32_t ph_a = d_s + (uint32_t)k * 8u;                 // 16 fp16 keys = 8 columns
+                    const uint32_t pl_a = d_s + TM_PLO + (uint32_t)k * 8u;
+                    umma_f16_ts(d_o, pl_a, vh, idesc_pv, k != 0 ? 1u : 0u);
+                    umma_f16_ts(d_o, ph_a, vl, idesc_pv, 1u);
+                    umma_f16_ts(d_o, ph_a, vh, idesc_pv, 1u);
                 }
                 umma_commit<1>(&v_empty[stage]);
                 umma_commit<1>(&o_full[stage]);

@@ -220,13 +220,16 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same smem offset in CTA `rank` of this cluster
+// arrive on the mbarrier at the same smem offset in CTA `rank` of this cluster.  Relaxed: the arrivals of this
+// library only hand tensor-memory buffers back to the MMA issuer and are ordered by tcgen05.fence; with
+// .release.cluster the compiler emits ERRBAR + CGAERRBAR in front of every arrive, which accounted for a
+// quarter of the GEMM epilogue warps' time (profiles/r1e_*).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
     asm volatile(
         "{\n\t"
         ".reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
         "}\n" ::"r"(smem_u32(bar)), "r"(rank)
         : "memory");
 }
