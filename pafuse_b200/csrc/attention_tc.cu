@@ -33,6 +33,7 @@
 
 #include <cudaTypedefs.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace pafuse {
 
@@ -40,9 +41,14 @@ namespace {
 
 constexpr int TILE_ROWS = 128;
 constexpr int ATT_THREADS = 384;
-// TMEM columns: stage s holds S (fp32, 128 columns) at s*128, overwritten in place by P_hi (64 columns of
-// packed fp16 pairs) and P_lo (next 64); O (fp32, HDP columns) at 256 + s*64
-constexpr uint32_t TM_S = 0, TM_PLO = 64, TM_O = 256;
+// TMEM columns, two layouts (AttnTcParams::tm_*):
+//   aliased (SEP = false): stage s holds S (fp32, 128 columns) at s*128, overwritten in place by P_hi (64 columns
+//     of packed fp16 pairs) and P_lo (next 64); O (fp32, HDP columns) at 256 + s*64.  QK^T of unit i+2 can only
+//     be issued after PV of unit i, and the softmax group waits for O of its unit before it starts the next one.
+//   separate (SEP = true, when O + S + P fit in 256 columns per stage): S, P_hi, P_lo and O do not overlap, so
+//     QK^T of unit i+2 is issued as soon as the softmax group has READ S of unit i, and the group writes out O of
+//     unit i-2 after the softmax of unit i: it never waits for the tensor pipe (the aliased version spent 45 % of
+//     its time waiting for PV, profiles/r1e_*).
 
 struct AttnTcParams {
     int num_tiles;
@@ -59,6 +65,8 @@ struct AttnTcParams {
     int chunk_bytes;          // 16, or 8 when a head slice is not 16-byte aligned in [token, C]
     int chunks_per_row;       // 2*hd / chunk_bytes
     int inv_cpr_q16;          // ceil(65536 / chunks_per_row)
+    // tensor-memory columns: S / P of stage s at tm_s0 + s * tm_stride_s (+ tm_phi_off / tm_plo_off), O at tm_o0 + s * tm_stride_o
+    int tm_s0, tm_stride_s, tm_phi_off, tm_plo_off, tm_o0, tm_stride_o;
     op_t* o_hi;
     op_t* o_lo;
 };
@@ -124,7 +132,7 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 }
 
 // HDP: tile row width in fp16 elements (64 / 32).  LT: compile-time group length (0 = use p.L; NCH_MAX chunks)
-template <int HDP, int LT>
+template <int HDP, int LT, bool SEP>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                     const AttnTcParams p) {
@@ -136,7 +144,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     constexpr int NCH_MAX = LT ? (LT + 31) / 32 : 4;           // 32-column score chunks of one group
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t qk_full[2], qk_empty[2], v_full[2], v_empty[2];
-    __shared__ __align__(8) uint64_t s_full[2], p_full[2], o_full[2], o_empty[2];
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2], p_full[2], o_full[2], o_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -164,6 +172,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             mbar_init(&v_full[s], 1);
             mbar_init(&v_empty[s], 1);
             mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], 4);
             mbar_init(&p_full[s], 4);                          // one lane per warp of the stage's softmax group
             mbar_init(&o_full[s], 1);
             mbar_init(&o_empty[s], 4);
@@ -230,14 +239,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             const uint32_t idesc_qk = make_idesc_f16(128, (uint32_t)(key_steps * 16));
             const uint32_t idesc_pv = make_idesc_f16(128, HDP) | (1u << 16);      // B (= V) is MN-major
             const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-            const uint32_t d_s = tmem_base + TM_S + (uint32_t)stage * 128u;
-            const uint32_t d_o = tmem_base + TM_O + (uint32_t)stage * 64u;
+            const uint32_t d_s = tmem_base + (uint32_t)(p.tm_s0 + stage * p.tm_stride_s);
+            const uint32_t d_o = tmem_base + (uint32_t)(p.tm_o0 + stage * p.tm_stride_o);
+            const uint32_t d_phi = d_s + (uint32_t)p.tm_phi_off, d_plo = d_s + (uint32_t)p.tm_plo_off;
             auto issue_qk = [&](int it) {
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(&qk_full[stage], ph);
+                if (SEP) mbar_wait(&s_empty[stage], ph ^ 1);   // the softmax group has read S of unit it-2
                 tcgen05_fence_after();
-                // S[stage] aliases P[stage] of unit it-2: that PV was issued by this thread before this point and
-                // the tensor pipe executes in issue order
+                // aliased layout: S[stage] overwrites P[stage] of unit it-2; that PV was issued by this thread
+                // before this point and the tensor pipe executes in issue order
 #pragma unroll
                 for (int k = 0; k < HDP / 16; ++k) {
                     const uint32_t ko = (uint32_t)k * 32u;
@@ -254,6 +265,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             if (stage < n_local) issue_qk(stage);
             for (int it = stage; it < n_local; it += 2) {
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                if (SEP && it + 2 < n_local) issue_qk(it + 2);
                 mbar_wait(&v_full[stage], ph);
                 mbar_wait(&o_empty[stage], ph ^ 1);            // the softmax group has read O of unit it-2
                 mbar_wait(&p_full[stage], ph);                 // P of this unit is in tensor memory
@@ -262,15 +274,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     const uint32_t vo = (uint32_t)k * 16u * ROWB;                 // 16 keys further down the V tile
                     const uint64_t vh = make_desc(sa + 4 * TILE_BYTES + vo, SBO, LAYOUT);
                     const uint64_t vl = make_desc(sa + 5 * TILE_BYTES + vo, SBO, LAYOUT);
-                    const uint32_t ph_a = d_s + (uint32_t)k * 8u;                 // 16 fp16 keys = 8 columns
-                    const uint32_t pl_a = d_s + TM_PLO + (uint32_t)k * 8u;
+                    const uint32_t ph_a = d_phi + (uint32_t)k * 8u;               // 16 fp16 keys = 8 columns
+                    const uint32_t pl_a = d_plo + (uint32_t)k * 8u;
                     umma_f16_ts(d_o, pl_a, vh, idesc_pv, k != 0 ? 1u : 0u);
                     umma_f16_ts(d_o, ph_a, vl, idesc_pv, 1u);
                     umma_f16_ts(d_o, ph_a, vh, idesc_pv, 1u);
                 }
                 umma_commit<1>(&v_empty[stage]);
                 umma_commit<1>(&o_full[stage]);
-                if (it + 2 < n_local) issue_qk(it + 2);
+                if (!SEP && it + 2 < n_local) issue_qk(it + 2);
             }
         }
     }
@@ -286,27 +298,51 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         const bool warp_live = g < p.G && row0_in_g < L;       // the warp holds at least one token row
         const int c0 = g * nch;                                // first 32-column score chunk of the group
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const uint32_t s_addr = tmem_base + lane_sel + TM_S + (uint32_t)wg * 128u;
-        const uint32_t o_addr = tmem_base + lane_sel + TM_O + (uint32_t)wg * 64u;
+        const uint32_t s_addr = tmem_base + lane_sel + (uint32_t)(p.tm_s0 + wg * p.tm_stride_s);
+        const uint32_t phi_addr = s_addr + (uint32_t)p.tm_phi_off, plo_addr = s_addr + (uint32_t)p.tm_plo_off;
+        const uint32_t o_addr = tmem_base + lane_sel + (uint32_t)(p.tm_o0 + wg * p.tm_stride_o);
         const float sc = p.scale_log2e;
         uint8_t* stg = smem + 2 * STAGE_BYTES + (warp - 4) * p.stg_warp_bytes;   // this warp's output staging rows
         uint8_t* my_row = stg + lane * p.stg_pitch;
         const int n_zero_chunks = (key_steps + 1) / 2;         // 32-key chunks the PV product reads
-        for (int it = wg; it < n_local; it += 2) {
+
+        // keys of the other groups: exact zeros in P.  The separate layout never overwrites them: once is enough.
+        auto zero_other_groups = [&]() {
+            uint32_t z[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] = 0u;
+            for (int c = 0; c < n_zero_chunks; ++c)
+                if (c < c0 || c >= c0 + nch) {
+                    tmem_st_32x16(phi_addr + (uint32_t)(c * 16), z);
+                    tmem_st_32x16(plo_addr + (uint32_t)(c * 16), z);
+                }
+        };
+        if (SEP && warp_live) {
+            zero_other_groups();
+            tmem_st_wait();
+        }
+
+        // ---- S -> P of unit `it`; returns the row sum
+        auto softmax_unit = [&](int it) -> float {
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-            const int u = (int)blockIdx.x + it * (int)gridDim.x;
-            const int tile = u >> 3, head = u & 7;
             mbar_wait(&s_full[wg], ph);
             tcgen05_fence_after();
             float sum = 0.f;
+            uint32_t sv[NCH_MAX * 32];
             if (warp_live) {
-                // ---- the scores of this row against the keys of its group, once, into registers
-                uint32_t sv[NCH_MAX * 32];
+                // the scores of this row against the keys of its group, once, into registers
 #pragma unroll
                 for (int k = 0; k < NCH_MAX; ++k)
                     if (k < nch) tmem_ld_32x32(s_addr + (uint32_t)((c0 + k) * 32), &sv[k * 32]);
                 tmem_ld_wait();
-                // ---- row maximum over the L live keys (four chains)
+            }
+            if (SEP) {                                         // S may be overwritten by QK^T of unit it+2
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[wg]);
+            }
+            if (warp_live) {
+                // row maximum over the L live keys (four chains)
                 float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
                 for (int k = 0; k < NCH_MAX; ++k)
@@ -316,7 +352,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                             if (k * 32 + i < L) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[k * 32 + i]));
                     }
                 const float moff = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
-                // ---- p = exp2(s*c - m*c), row sum, fp16 hi/lo over the scores
+                // p = exp2(s*c - m*c), row sum, fp16 hi/lo
                 float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int k = 0; k < NCH_MAX; ++k)
@@ -330,27 +366,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                             s4[i & 3] += p0 + p1;
                             split_pair(p0, p1, hi16[i], lo16[i]);
                         }
-                        tmem_st_32x16(s_addr + (uint32_t)((c0 + k) * 16), hi16);
-                        tmem_st_32x16(s_addr + TM_PLO + (uint32_t)((c0 + k) * 16), lo16);
+                        tmem_st_32x16(phi_addr + (uint32_t)((c0 + k) * 16), hi16);
+                        tmem_st_32x16(plo_addr + (uint32_t)((c0 + k) * 16), lo16);
                     }
                 sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-                {
-                    uint32_t z[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) z[i] = 0u;
-                    for (int c = 0; c < n_zero_chunks; ++c)    // keys of the other groups: exact zeros
-                        if (c < c0 || c >= c0 + nch) {
-                            tmem_st_32x16(s_addr + (uint32_t)(c * 16), z);
-                            tmem_st_32x16(s_addr + TM_PLO + (uint32_t)(c * 16), z);
-                        }
-                }
+                if (!SEP) zero_other_groups();
                 tmem_st_wait();
             }
             // rows of a dead warp feed stale bits into rows of O nobody stores: nothing to write for them
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[wg]);
-            // ---- output: O / sum -> fp16 hi/lo -> global
+            return sum;
+        };
+
+        // ---- O of unit `it` / sum -> fp16 hi/lo -> global
+        auto output_unit = [&](int it, float sum) {
+            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            const int u = (int)blockIdx.x + it * (int)gridDim.x;
+            const int tile = u >> 3, head = u & 7;
             mbar_wait(&o_full[wg], ph);
             tcgen05_fence_after();
             uint32_t ov[HDP];
@@ -362,7 +396,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_empty[wg]);
-            if (!warp_live) continue;
+            if (!warp_live) return;
             // token of staging row i of this warp = tok0 + i * tstride, for i < n_rows (all warp-uniform)
             long long tok0;
             int tstride, n_rows = min(32, L - row0_in_g);
@@ -406,6 +440,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
                 }
             }
+        };
+
+        if (!SEP) {
+            for (int it = wg; it < n_local; it += 2) {
+                const float sum = softmax_unit(it);
+                output_unit(it, sum);
+            }
+        } else {
+            // software pipeline: the output of unit it-2 (its PV ran during the softmax of unit it) follows the
+            // softmax of unit it
+            float prev_sum = 1.f;
+            int prev = -1;
+            for (int it = wg; it < n_local; it += 2) {
+                const float sum = softmax_unit(it);
+                if (prev >= 0) output_unit(prev, prev_sum);
+                prev = it;
+                prev_sum = sum;
+            }
+            if (prev >= 0) output_unit(prev, prev_sum);
         }
     }
 
@@ -419,6 +472,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
 PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
 int g_sms = 0;
+int g_sep_mode = 2;      // PAFUSE_ATT_SEP: 0 aliased layout only, 1 separate when it fits, 2 also with one group less
 
 int att_init() {
     if (g_enc) return 0;
@@ -433,6 +487,7 @@ int att_init() {
     int dev = 0;
     PAFUSE_CUDA_OK(cudaGetDevice(&dev));
     PAFUSE_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (const char* e = getenv("PAFUSE_ATT_SEP")) g_sep_mode = atoi(e);
     return 0;
 }
 
@@ -468,14 +523,14 @@ int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int h
     return 0;
 }
 
-template <int HDP, int LT>
+template <int HDP, int LT, bool SEP>
 int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, cudaStream_t st) {
     const int SMEM = 2 * 6 * TILE_ROWS * HDP * 2 + 8 * p.stg_warp_bytes + 1024;
     if (SMEM > 227 * 1024) {
         set_last_error("attention_tc: head_dim %d needs %d bytes of shared memory", p.hd, SMEM);
         return -1;
     }
-    auto kern = attention_tc_kernel<HDP, LT>;
+    auto kern = attention_tc_kernel<HDP, LT, SEP>;
     static int configured = 0;
     if (configured < SMEM) {
         PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -506,6 +561,35 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
     p.L = L;
     p.Lp = (L + 31) / 32 * 32;
     p.G = 128 / p.Lp;
+    // tensor-memory layout: separate S / P / O regions when they fit in 256 columns per stage (if necessary with
+    // one group less per tile), else the aliased layout
+    bool sep = false;
+    if (g_sep_mode > 0) {
+        for (int G = p.G; G >= 1 && G >= p.G - (g_sep_mode > 1 ? 1 : 0); --G) {
+            const int s_cols = G * p.Lp;
+            const int key_steps = ((G - 1) * p.Lp + L + 15) / 16;
+            const int p_half = (key_steps + 1) / 2 * 16;
+            if (hdp + s_cols + 2 * p_half <= 256) {
+                sep = true;
+                p.G = G;
+                p.tm_o0 = 0;
+                p.tm_stride_o = 256;
+                p.tm_s0 = hdp;
+                p.tm_stride_s = 256;
+                p.tm_phi_off = s_cols;
+                p.tm_plo_off = s_cols + p_half;
+                break;
+            }
+        }
+    }
+    if (!sep) {
+        p.tm_s0 = 0;
+        p.tm_stride_s = 128;
+        p.tm_phi_off = 0;
+        p.tm_plo_off = 64;
+        p.tm_o0 = 256;
+        p.tm_stride_o = 64;
+    }
     p.hd = hd;
     p.C = C;
     p.J = J;
@@ -531,15 +615,19 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
     if (int rc = make_plane_map(&mh, pl.hi, pl.rows_cap, hds, hdp, temporal != 0, J, F, S, p.G, L, p.Lp)) return rc;
     if (int rc = make_plane_map(&ml, pl.lo, pl.rows_cap, hds, hdp, temporal != 0, J, F, S, p.G, L, p.Lp)) return rc;
     // the group lengths of the H3WB parts get compile-time masks; anything else runs the generic instance
-    if (hdp == 64) {
-        if (L == 24) return launch_tc<64, 24>(mh, ml, p, st);
-        if (L == 27) return launch_tc<64, 27>(mh, ml, p, st);
-        return launch_tc<64, 0>(mh, ml, p, st);
-    }
-    if (L == 68) return launch_tc<32, 68>(mh, ml, p, st);
-    if (L == 42) return launch_tc<32, 42>(mh, ml, p, st);
-    if (L == 27) return launch_tc<32, 27>(mh, ml, p, st);
-    return launch_tc<32, 0>(mh, ml, p, st);
+#define PAFUSE_ATT_CASE(HDPV, LV)                                                             \
+    if (hdp == HDPV && (LV == 0 || L == LV))                                                  \
+        return sep ? launch_tc<HDPV, LV, true>(mh, ml, p, st) : launch_tc<HDPV, LV, false>(mh, ml, p, st);
+    PAFUSE_ATT_CASE(64, 24)
+    PAFUSE_ATT_CASE(64, 27)
+    PAFUSE_ATT_CASE(64, 0)
+    PAFUSE_ATT_CASE(32, 68)
+    PAFUSE_ATT_CASE(32, 42)
+    PAFUSE_ATT_CASE(32, 27)
+    PAFUSE_ATT_CASE(32, 0)
+#undef PAFUSE_ATT_CASE
+    set_last_error("attention_tc: no kernel instance for hdp=%d", hdp);
+    return -1;
 }
 
 // fp32 qkv [M,3C] -> head planes (unit tests; the production path gets the planes from the qkv GEMM epilogue)
