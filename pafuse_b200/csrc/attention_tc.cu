@@ -157,6 +157,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     const int n_local = (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int rows_box = p.G * Lp;                             // tile rows every TMA box writes (96 or 128)
     const int key_steps = ((p.G - 1) * Lp + L + 15) / 16;      // 16-key MMA steps that can hold live keys
+    // softmax warps (one per 32 tile rows) that hold at least one token row; the others take no part in the
+    // barrier protocol (a warp without work could run a unit ahead and arrive twice in one phase)
+    int n_live = 0;
+    for (int q = 0; q < 4; ++q) {
+        const int g = (q * 32) / Lp;
+        n_live += (g < p.G && q * 32 - g * Lp < L) ? 1 : 0;
+    }
 
     // rows no box ever writes must not hold NaN bit patterns (0 * NaN in the PV product)
     for (int i = threadIdx.x; i < 2 * STAGE_BYTES / 16; i += ATT_THREADS)
@@ -172,10 +179,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             mbar_init(&v_full[s], 1);
             mbar_init(&v_empty[s], 1);
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], 4);
-            mbar_init(&p_full[s], 4);                          // one lane per warp of the stage's softmax group
+            mbar_init(&s_empty[s], n_live);
+            mbar_init(&p_full[s], n_live);                     // one lane per live warp of the stage's softmax group
             mbar_init(&o_full[s], 1);
-            mbar_init(&o_empty[s], 4);
+            mbar_init(&o_empty[s], n_live);
         }
         fence_barrier_init();
     }
@@ -352,6 +359,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                             if (k * 32 + i < L) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[k * 32 + i]));
                     }
                 const float moff = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
+                if (SEP && it >= 2) {
+                    // P of this unit overwrites P of unit it-2: its PV must have retired.  (This also keeps p_full
+                    // from running two phases ahead of the issuer, which would wait for ever on a parity.)
+                    mbar_wait(&o_full[wg], (uint32_t)((it - 2) >> 1) & 1u);
+                    tcgen05_fence_after();
+                }
                 // p = exp2(s*c - m*c), row sum, fp16 hi/lo
                 float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -442,7 +455,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             }
         };
 
-        if (!SEP) {
+        if (!warp_live) {
+            // no rows: nothing to compute, nothing to signal
+        } else if (!SEP) {
             for (int it = wg; it < n_local; it += 2) {
                 const float sum = softmax_unit(it);
                 output_unit(it, sum);
