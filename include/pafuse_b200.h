@@ -145,6 +145,9 @@ int pafuse_qkv_attention(pafuse_ctx* ctx, const float* x, const float* w, const 
 int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable);
 /* debugging switch: CUDA-core attention kernel instead of the tcgen05 one */
 int pafuse_set_debug_simt_attention(pafuse_ctx* ctx, int32_t enable);
+/* 1 (default): the LayerNorms that follow the proj / fc2 GEMMs are computed in their epilogues for parts whose
+ * channel width fits one output tile (C <= 256); 0: separate LayerNorm launches everywhere */
+int pafuse_set_fuse_layernorm(pafuse_ctx* ctx, int32_t enable);
 /* process-wide: 2 (default) = tcgen05 CTA pairs (cta_group::2, 256-row tiles), 1 = lone CTAs */
 int pafuse_set_gemm_cta_group(int32_t cta_group);
 /* process-wide: 1 (default) = weight-stationary GEMM tiles where the W slice fits in shared memory, 0 = always stream W */

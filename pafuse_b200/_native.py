@@ -53,6 +53,7 @@ _SIGNATURES = {
     "pafuse_set_debug_simt_gemm": (c_int32, [c_void_p, c_int32]),
     "pafuse_set_gemm_cta_group": (c_int32, [c_int32]),
     "pafuse_set_gemm_weight_stationary": (c_int32, [c_int32]),
+    "pafuse_set_fuse_layernorm": (c_int32, [c_void_p, c_int32]),
     "pafuse_set_debug_simt_attention": (c_int32, [c_void_p, c_int32]),
 }
 
@@ -273,6 +274,9 @@ class NativeContext:
     def set_gemm_cta_group(self, cta_group: int):
         with torch.cuda.device(self.device):
             check(self.lib.pafuse_set_gemm_cta_group(int(cta_group)), "pafuse_set_gemm_cta_group")
+
+    def set_fuse_layernorm(self, enable: bool):
+        check(self.lib.pafuse_set_fuse_layernorm(self.handle, 1 if enable else 0), "pafuse_set_fuse_layernorm")
 
     def set_gemm_weight_stationary(self, enable: bool):
         with torch.cuda.device(self.device):

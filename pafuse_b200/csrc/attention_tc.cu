@@ -64,7 +64,7 @@ struct AttnTcParams {
     int stg_warp_bytes;       // 32 staging rows, rounded up to 128 B
     int chunk_bytes;          // 16, or 8 when a head slice is not 16-byte aligned in [token, C]
     int chunks_per_row;       // 2*hd / chunk_bytes
-    int inv_cpr_q16;          // ceil(65536 / chunks_per_row)
+    int rows_per_iter;        // 32 / chunks_per_row: staging rows one copy-out instruction of a warp covers
     // tensor-memory columns: S / P of stage s at tm_s0 + s * tm_stride_s (+ tm_phi_off / tm_plo_off), O at tm_o0 + s * tm_stride_o
     int tm_s0, tm_stride_s, tm_phi_off, tm_plo_off, tm_o0, tm_stride_o;
     op_t* o_hi;
@@ -312,6 +312,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         uint8_t* stg = smem + 2 * STAGE_BYTES + (warp - 4) * p.stg_warp_bytes;   // this warp's output staging rows
         uint8_t* my_row = stg + lane * p.stg_pitch;
         const int n_zero_chunks = (key_steps + 1) / 2;         // 32-key chunks the PV product reads
+        const int cp_row = lane / p.chunks_per_row;            // copy-out role of this lane
+        const int cp_cc = lane - cp_row * p.chunks_per_row;
+        const bool cp_active = cp_row < p.rows_per_iter;
+        const int cp_src = cp_row * p.stg_pitch + cp_cc * p.chunk_bytes;
 
         // keys of the other groups: exact zeros in P.  The separate layout never overwrites them: once is enough.
         auto zero_other_groups = [&]() {
@@ -359,12 +363,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                             if (k * 32 + i < L) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[k * 32 + i]));
                     }
                 const float moff = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
-                if (SEP && it >= 2) {
-                    // P of this unit overwrites P of unit it-2: its PV must have retired.  (This also keeps p_full
-                    // from running two phases ahead of the issuer, which would wait for ever on a parity.)
-                    mbar_wait(&o_full[wg], (uint32_t)((it - 2) >> 1) & 1u);
-                    tcgen05_fence_after();
-                }
                 // p = exp2(s*c - m*c), row sum, fp16 hi/lo
                 float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -378,6 +376,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                             if (k * 32 + 2 * i + 1 < L) p1 = fast_exp2(fmaf(__uint_as_float(sv[k * 32 + 2 * i + 1]), sc, -moff));
                             s4[i & 3] += p0 + p1;
                             split_pair(p0, p1, hi16[i], lo16[i]);
+                        }
+                        if (SEP && k == 0 && it >= 2) {
+                            // P of this unit overwrites P of unit it-2: its PV must have retired (it ran during the
+                            // output of unit it-4 and the exponentials above).  This also keeps p_full from running
+                            // two phases ahead of the issuer, which would then wait for ever on a parity.
+                            mbar_wait(&o_full[wg], (uint32_t)((it - 2) >> 1) & 1u);
+                            tcgen05_fence_after();
                         }
                         tmem_st_32x16(phi_addr + (uint32_t)((c0 + k) * 16), hi16);
                         tmem_st_32x16(plo_addr + (uint32_t)((c0 + k) * 16), lo16);
@@ -433,7 +438,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 #pragma unroll
             for (int i = 0; i < HDP / 2; ++i)
                 split_pair(__uint_as_float(ov[2 * i]) * inv, __uint_as_float(ov[2 * i + 1]) * inv, oh[i], ol[i]);
-            const int n_chunks = n_rows * p.chunks_per_row;
+            // copy-out: lane -> (row lane / cpr of the current group of rows_per_iter rows, chunk lane % cpr); the
+            // per-chunk index arithmetic of the first version (64-bit multiplies per 8 bytes) cost as many
+            // instructions as the softmax itself (profiles/r1h_*)
+            const size_t row_bytes = (size_t)tstride * (size_t)(p.C * 2);
+            const size_t dst0 = (size_t)tok0 * (size_t)(p.C * 2) + (size_t)(head * p.hd * 2 + cp_cc * p.chunk_bytes) +
+                                (size_t)cp_row * row_bytes;
+            const size_t dst_step = (size_t)p.rows_per_iter * row_bytes;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 __syncwarp();                                  // the previous copy-out has read the staging rows
@@ -443,14 +454,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                         *reinterpret_cast<uint2*>(my_row + 8 * i) =
                             half == 0 ? make_uint2(oh[2 * i], oh[2 * i + 1]) : make_uint2(ol[2 * i], ol[2 * i + 1]);
                 __syncwarp();
-                uint8_t* obase = reinterpret_cast<uint8_t*>((half == 0 ? p.o_hi : p.o_lo) + head * p.hd);
-                for (int k = lane; k < n_chunks; k += 32) {
-                    const int row = (k * p.inv_cpr_q16) >> 16;                 // k / chunks_per_row
-                    const int cc = k - row * p.chunks_per_row;
-                    const uint8_t* src = stg + row * p.stg_pitch + cc * p.chunk_bytes;
-                    uint8_t* dst = obase + (size_t)(tok0 + (long long)row * tstride) * (size_t)(p.C * 2) + cc * p.chunk_bytes;
-                    if (p.chunk_bytes == 16) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
-                    else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+                uint8_t* dst = reinterpret_cast<uint8_t*>(half == 0 ? p.o_hi : p.o_lo) + dst0;
+                const uint8_t* src = stg + cp_src;
+                for (int row = cp_row; row < n_rows; row += p.rows_per_iter) {
+                    if (cp_active) {
+                        if (p.chunk_bytes == 16) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+                        else *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+                    }
+                    dst += dst_step;
+                    src += p.rows_per_iter * p.stg_pitch;
                 }
             }
         };
@@ -487,7 +499,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
 PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
 int g_sms = 0;
-int g_sep_mode = 2;      // PAFUSE_ATT_SEP: 0 aliased layout only, 1 separate when it fits, 2 also with one group less
+int g_sep_mode = 1;      // PAFUSE_ATT_SEP: 0 aliased layout only, 1 separate when it fits (default), 2 also with one group less per tile (slower: measured)
 
 int att_init() {
     if (g_enc) return 0;
@@ -625,7 +637,7 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
     p.stg_warp_bytes = (32 * p.stg_pitch + 127) / 128 * 128;
     p.chunk_bytes = (2 * hd) % 16 == 0 ? 16 : 8;              // hd % 4 == 0, so a slice is at least 8-byte aligned
     p.chunks_per_row = 2 * hd / p.chunk_bytes;
-    p.inv_cpr_q16 = (65536 + p.chunks_per_row - 1) / p.chunks_per_row;
+    p.rows_per_iter = 32 / p.chunks_per_row;
     CUtensorMap mh, ml;
     if (int rc = make_plane_map(&mh, pl.hi, pl.rows_cap, hds, hdp, temporal != 0, J, F, S, p.G, L, p.Lp)) return rc;
     if (int rc = make_plane_map(&ml, pl.lo, pl.rows_cap, hds, hdp, temporal != 0, J, F, S, p.G, L, p.Lp)) return rc;

@@ -63,6 +63,7 @@ struct KernelParams {
     const float* bias;
     int hds;                         // EPI_PLANES: stored head width (columns per plane)
     int plane_pw;                    // EPI_PLANES: columns per output box, 32 (hds % 32 == 0) or 16
+    GemmLnFuse ln;                   // EPI_RESID_LN
 };
 
 // Tile walk of one CTA group.  Streaming mode: tiles (m, n) in m-major order, strided over the groups, so
@@ -100,13 +101,236 @@ struct TileWalk {
     }
 };
 
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t r[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait_all() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// Epilogue of the residual GEMMs (proj, fc2) of the parts whose rows fit one tile (N == BN <= 256), fused with the
+// LayerNorms that follow them (mixste.py:114-115 norm2; :243,257,269,273 the shared norm that closes the block,
+// :250 Temporal_pos_embed, and norm1 of the next block):
+//     v  = x + acc * scale + bias                                   (x: fp32 residual stream, read here)
+//     not chained:  x <- v ;                          a = LN(v; g1, b1)   -> fp16 hi/lo
+//     chained:      x <- y = LN(v; g0, b0) [+ add_f[f]] ;  a = LN(y; g1, b1)   -> fp16 hi/lo
+// It replaces the L2-side reduction of EPI_RESID plus one ln_chain_kernel launch (8-12 B per element of DRAM
+// traffic).  A thread owns one row (= TMEM lane); the two warps of a lane quarter split the 32-column chunks
+// (even / odd) and exchange their partial row sums through shared memory.  The row values stay in the
+// accumulator's tensor memory between the passes (tcgen05.st / tcgen05.ld), statistics are two-pass like
+// ln_chain_kernel.  x is fetched with coalesced 16-byte loads one chunk ahead (registers), transposed through the
+// warp's staging box, which then carries the output row by row to the TMA store.
+// coalesced fetch of a 32 x 32 box of x: lane -> 16 bytes at column (lane & 7) * 4 of rows (lane >> 3) + 4 i
+__device__ __forceinline__ void ln_fetch_x(const KernelParams& p, float4 (&xr)[8], int row0, int c0, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long r = (long long)row0 + (lane >> 3) + 4 * i;
+        xr[i] = r < p.M ? __ldg(reinterpret_cast<const float4*>(p.ln.x + (size_t)r * p.N + c0 + (lane & 7) * 4))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int CG>
+__device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const CUtensorMap& tm_x, const CUtensorMap& tm_hi,
+                                                  const CUtensorMap& tm_lo, uint8_t* box, float* xch, uint32_t t_base,
+                                                  int row0, int q, int half, int lane, int BN, float oscale,
+                                                  uint64_t* tmem_empty, float4 (&xr)[8]) {
+    const GemmLnFuse& f = p.ln;
+    const int N = p.N;
+    const int nchunks = (BN / 32 - half + 1) / 2;                     // chunks half, half + 2, ...
+    const bool chained = f.g0 != nullptr;
+    const float invN = 1.0f / (float)N;
+    float* my_x = xch + (q * 32 + lane) * 2;
+    const int bar_id = 1 + q;
+    uint8_t* rowp = box + lane * 128;
+    const int sw = lane & 7;
+
+    auto fetch_x = [&](int c0) { ln_fetch_x(p, xr, row0, c0, lane); };
+    auto exchange = [&](float v) -> float {                           // sum over the two warps that share this row
+        my_x[half] = v;
+        pair_bar_sync(bar_id);
+        const float o = my_x[half ^ 1];
+        pair_bar_sync(bar_id);                                        // the slot may be rewritten after this point
+        return v + o;
+    };
+    auto stats = [&](float mean, float eps) -> float {                // second pass: 1 / sqrt(var + eps)
+        float sq = 0.f;
+        for (int ci = 0; ci < nchunks; ++ci) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_base + (uint32_t)((half + 2 * ci) * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float d = __uint_as_float(r[i]) - mean;
+                sq = fmaf(d, d, sq);
+            }
+        }
+        return 1.0f / sqrtf(exchange(sq) * invN + eps);
+    };
+    // LN(v; g, b) of the row values held in tensor memory -> fp16 hi/lo boxes -> TMA stores
+    auto emit_split = [&](float mean, float rstd, const float* g, const float* b) {
+        const float mr = -mean * rstd;
+        for (int ci = 0; ci < nchunks; ++ci) {
+            const int c0 = (half + 2 * ci) * 32;
+            uint32_t r[32];
+            tmem_ld_32x32(t_base + (uint32_t)c0, r);
+            if (lane == 0) bulk_wait_group_read<0>();
+            tmem_ld_wait();
+            __syncwarp();
+            const float4* g4 = reinterpret_cast<const float4*>(g + c0);
+            const float4* b4 = reinterpret_cast<const float4*>(b + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 ga = __ldg(g4 + 2 * i), gb = __ldg(g4 + 2 * i + 1);
+                const float4 ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
+                float v[8];
+                v[0] = fmaf(fmaf(__uint_as_float(r[8 * i + 0]), rstd, mr), ga.x, ba.x);
+                v[1] = fmaf(fmaf(__uint_as_float(r[8 * i + 1]), rstd, mr), ga.y, ba.y);
+                v[2] = fmaf(fmaf(__uint_as_float(r[8 * i + 2]), rstd, mr), ga.z, ba.z);
+                v[3] = fmaf(fmaf(__uint_as_float(r[8 * i + 3]), rstd, mr), ga.w, ba.w);
+                v[4] = fmaf(fmaf(__uint_as_float(r[8 * i + 4]), rstd, mr), gb.x, bb.x);
+                v[5] = fmaf(fmaf(__uint_as_float(r[8 * i + 5]), rstd, mr), gb.y, bb.y);
+                v[6] = fmaf(fmaf(__uint_as_float(r[8 * i + 6]), rstd, mr), gb.z, bb.z);
+                v[7] = fmaf(fmaf(__uint_as_float(r[8 * i + 7]), rstd, mr), gb.w, bb.w);
+                uint2 h0, l0, h1, l1;
+                split_pair_sat(v[0], v[1], h0.x, l0.x);
+                split_pair_sat(v[2], v[3], h0.y, l0.y);
+                split_pair_sat(v[4], v[5], h1.x, l1.x);
+                split_pair_sat(v[6], v[7], h1.y, l1.y);
+                const int off = lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);   // 32 rows x 64 B, 64-byte swizzle
+                *reinterpret_cast<uint4*>(box + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                *reinterpret_cast<uint4*>(box + 2048 + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tm_hi, box, c0, row0);
+                tma_store_2d(&tm_lo, box + 2048, c0, row0);
+                bulk_commit_group();
+            }
+        }
+    };
+
+    // ---- pass 1: v = x + acc * scale + bias -> tensor memory (and, when not chained, -> x)
+    float sum = 0.f;
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int c0 = (half + 2 * ci) * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(t_base + (uint32_t)c0, r);
+        if (lane == 0) bulk_wait_group_read<0>();                     // the store that last used the box has read it
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                                 // transpose through the box (128-byte swizzle)
+            const int rr = (lane >> 3) + 4 * i;
+            *reinterpret_cast<float4*>(box + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)) = xr[i];
+        }
+        __syncwarp();
+        if (ci + 1 < nchunks) fetch_x(c0 + 64);                       // next chunk's x, in flight during the math
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4* slot = reinterpret_cast<float4*>(rowp + ((i ^ sw) << 4));
+            const float4 xv = *slot;
+            const float4 bb = __ldg(b4 + i);
+            float4 v;
+            v.x = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bb.x) + xv.x;
+            v.y = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bb.y) + xv.y;
+            v.z = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bb.z) + xv.z;
+            v.w = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bb.w) + xv.w;
+            sum += (v.x + v.y) + (v.z + v.w);
+            r[4 * i + 0] = __float_as_uint(v.x);
+            r[4 * i + 1] = __float_as_uint(v.y);
+            r[4 * i + 2] = __float_as_uint(v.z);
+            r[4 * i + 3] = __float_as_uint(v.w);
+            if (!chained) *slot = v;
+        }
+        tmem_st_32x32(t_base + (uint32_t)c0, r);
+        if (!chained) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tm_x, box, c0, row0);
+                bulk_commit_group();
+            }
+        }
+    }
+    tmem_st_wait_all();
+    float mean = exchange(sum) * invN;
+    float rstd = stats(mean, chained ? f.eps0 : f.eps1);
+
+    if (chained) {
+        // ---- y = LN(v; g0, b0) [+ add_f[f]] -> x and tensor memory
+        const float mr = -mean * rstd;
+        const long long row = (long long)row0 + lane;
+        const float* addr = f.add_f ? f.add_f + (size_t)((row / f.J) % f.F) * N : nullptr;
+        float sum1 = 0.f;
+        for (int ci = 0; ci < nchunks; ++ci) {
+            const int c0 = (half + 2 * ci) * 32;
+            uint32_t r[32];
+            tmem_ld_32x32(t_base + (uint32_t)c0, r);
+            if (lane == 0) bulk_wait_group_read<0>();
+            tmem_ld_wait();
+            __syncwarp();
+            const float4* g4 = reinterpret_cast<const float4*>(f.g0 + c0);
+            const float4* b4 = reinterpret_cast<const float4*>(f.b0 + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 gg = __ldg(g4 + i), bb = __ldg(b4 + i);
+                float4 y;
+                y.x = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), rstd, mr), gg.x, bb.x);
+                y.y = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), rstd, mr), gg.y, bb.y);
+                y.z = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), rstd, mr), gg.z, bb.z);
+                y.w = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), rstd, mr), gg.w, bb.w);
+                if (addr) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(addr + c0) + i);
+                    y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w;
+                }
+                sum1 += (y.x + y.y) + (y.z + y.w);
+                r[4 * i + 0] = __float_as_uint(y.x);
+                r[4 * i + 1] = __float_as_uint(y.y);
+                r[4 * i + 2] = __float_as_uint(y.z);
+                r[4 * i + 3] = __float_as_uint(y.w);
+                *reinterpret_cast<float4*>(rowp + ((i ^ sw) << 4)) = y;
+            }
+            tmem_st_32x32(t_base + (uint32_t)c0, r);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tm_x, box, c0, row0);
+                bulk_commit_group();
+            }
+        }
+        tmem_st_wait_all();
+        mean = exchange(sum1) * invN;
+        rstd = stats(mean, f.eps1);
+    }
+    emit_split(mean, rstd, f.g1, f.b1);
+
+    // the accumulator buffer goes back to the MMA issuer
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        if (CG == 1) mbar_arrive(tmem_empty);
+        else mbar_arrive_cluster(tmem_empty, 0);
+    }
+}
+
 template <int EPI, int CG, bool WRES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                   const __grid_constant__ CUtensorMap tm_out0, const __grid_constant__ CUtensorMap tm_out1,
-                  const KernelParams p) {
+                  const __grid_constant__ CUtensorMap tm_out2, const KernelParams p) {
     extern __shared__ uint8_t smem_raw[];
+    __shared__ float ln_xch[EPI == EPI_RESID_LN ? 128 * 2 : 2];   // partial row sums of the two warps that share a row
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
@@ -138,7 +362,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         prefetch_tensormap(&tm_w_hi);
         prefetch_tensormap(&tm_w_lo);
         prefetch_tensormap(&tm_out0);
-        if (EPI == EPI_GELU_SPLIT || EPI == EPI_PLANES) prefetch_tensormap(&tm_out1);
+        if (EPI == EPI_GELU_SPLIT || EPI == EPI_PLANES || EPI == EPI_RESID_LN) prefetch_tensormap(&tm_out1);
+        if (EPI == EPI_RESID_LN) prefetch_tensormap(&tm_out2);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -282,10 +507,19 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         for (int it = 0; it < walk.count; ++it) {
             int m_tile, n_tile;
             walk.at(it, m_tile, n_tile);
+            const int row0 = (m_tile * CG + (int)cta_rank) * BM + q * 32;   // first row of this warp's box
+            float4 xr[8];                                             // EPI_RESID_LN: x of the next chunk
+            if (EPI == EPI_RESID_LN) ln_fetch_x(p, xr, row0, half * 32, lane);   // in flight while the main loop finishes
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
-            const int row0 = (m_tile * CG + (int)cta_rank) * BM + q * 32;   // first row of this warp's box
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+            if (EPI == EPI_RESID_LN) {
+                epilogue_resid_ln<CG>(p, tm_out0, tm_out1, tm_out2, box, ln_xch, t_base, row0, q, half, lane, BN, oscale,
+                                      &tmem_empty_bar[acc], xr);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                continue;
+            }
             if (half * 32 >= BN) {                                    // a 32-column tile has no odd chunk: nothing to read
                 tcgen05_fence_before();
                 __syncwarp();
@@ -453,12 +687,12 @@ int make_map_planes(CUtensorMap* map, const void* ptr, long long rows_cap, int h
 int g_num_sms = 0;
 int g_force_cg = 0;      // PAFUSE_GEMM_CTA_GROUP=1|2 overrides the default (2)
 int g_wres_enabled = 1;  // PAFUSE_GEMM_WRES=0 disables the weight-stationary mode
-int g_wres_min_stages = 3;
+int g_wres_min_stages = 4;  // with 3 stages (C = 384) the resident mode was slower than streaming (profiles/r1g_*)
 
 template <int EPI, int CG, bool WRES>
 int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
-               const CUtensorMap& o0, const CUtensorMap& o1, const KernelParams& kp, int grid, int smem,
-               cudaStream_t st) {
+               const CUtensorMap& o0, const CUtensorMap& o1, const CUtensorMap& o2, const KernelParams& kp, int grid,
+               int smem, cudaStream_t st) {
     auto kern = gemm_f16x3_kernel<EPI, CG, WRES>;
     static bool configured = false;                                   // per template instance
     if (!configured) {
@@ -477,16 +711,17 @@ int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PAFUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ah, al, wh, wl, o0, o1, kp));
+    PAFUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ah, al, wh, wl, o0, o1, o2, kp));
     PAFUSE_LAUNCH_OK();
     return 0;
 }
 
 template <int EPI, int CG>
 int launch_mode(bool wres, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
-                const CUtensorMap& o0, const CUtensorMap& o1, const KernelParams& kp, int grid, int smem, cudaStream_t st) {
-    return wres ? launch_epi<EPI, CG, true>(ah, al, wh, wl, o0, o1, kp, grid, smem, st)
-                : launch_epi<EPI, CG, false>(ah, al, wh, wl, o0, o1, kp, grid, smem, st);
+                const CUtensorMap& o0, const CUtensorMap& o1, const CUtensorMap& o2, const KernelParams& kp, int grid,
+                int smem, cudaStream_t st) {
+    return wres ? launch_epi<EPI, CG, true>(ah, al, wh, wl, o0, o1, o2, kp, grid, smem, st)
+                : launch_epi<EPI, CG, false>(ah, al, wh, wl, o0, o1, o2, kp, grid, smem, st);
 }
 
 template <int CG>
@@ -507,6 +742,14 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     kp.bias = g.bias;
     kp.hds = g.planes.hds;
     kp.plane_pw = g.planes.hds % 32 == 0 ? 32 : 16;
+    kp.ln = g.ln;
+    if (g.epilogue == EPI_RESID_LN) {
+        if (!gemm_can_fuse_ln(g.N) || kp.n_tiles != 1 || !g.ln.x || g.ln.x != g.out_f32 || !g.ln.g1 || !g.ln.b1 ||
+            !g.out_hi || !g.out_lo || (g.ln.g0 && !g.ln.b0)) {
+            set_last_error("gemm: EPI_RESID_LN needs N <= 256 in one tile, x == out_f32 and the norm parameters (N=%d)", g.N);
+            return -1;
+        }
+    }
     const int max_groups = g_num_sms / CG;
     const int WN = BN / CG;
 
@@ -542,8 +785,12 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     if (int rc = make_map_f16(&al, g.a_lo, g.M, g.K, BM, kp.a_bk)) return rc;
     if (int rc = make_map_f16(&wh, g.w_hi, g.N, g.K, WN)) return rc;
     if (int rc = make_map_f16(&wl, g.w_lo, g.N, g.K, WN)) return rc;
-    CUtensorMap o0, o1;
-    if (g.epilogue == EPI_PLANES) {
+    CUtensorMap o0, o1, o2;
+    if (g.epilogue == EPI_RESID_LN) {
+        if (int rc = make_map_out(&o0, g.out_f32, g.M, g.N, true)) return rc;
+        if (int rc = make_map_out(&o1, g.out_hi, g.M, g.N, false)) return rc;
+        if (int rc = make_map_out(&o2, g.out_lo, g.M, g.N, false)) return rc;
+    } else if (g.epilogue == EPI_PLANES) {
         if (g.planes.hds < 16 || g.planes.hds % 16 != 0 || g.N != 24 * g.planes.hds || g.planes.rows_cap < g.M) {
             set_last_error("gemm: bad head planes (hds=%d N=%d rows_cap=%lld M=%lld)", g.planes.hds, g.N, g.planes.rows_cap, g.M);
             return -1;
@@ -557,6 +804,7 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
         if (int rc = make_map_out(&o0, g.out_f32, g.M, g.N, true)) return rc;
         o1 = o0;
     }
+    if (g.epilogue != EPI_RESID_LN) o2 = o0;
     const int smem = kp.w_res_bytes + kp.stages * kp.stage_bytes + STG_BYTES + 1024;
     int grid;
     if (wres) {
@@ -566,10 +814,11 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
         grid = (int)(tiles < max_groups ? tiles : max_groups) * CG;
     }
     switch (g.epilogue) {
-        case EPI_F32: return launch_mode<EPI_F32, CG>(wres, ah, al, wh, wl, o0, o1, kp, grid, smem, st);
-        case EPI_GELU_SPLIT: return launch_mode<EPI_GELU_SPLIT, CG>(wres, ah, al, wh, wl, o0, o1, kp, grid, smem, st);
-        case EPI_RESID: return launch_mode<EPI_RESID, CG>(wres, ah, al, wh, wl, o0, o1, kp, grid, smem, st);
-        case EPI_PLANES: return launch_mode<EPI_PLANES, CG>(wres, ah, al, wh, wl, o0, o1, kp, grid, smem, st);
+        case EPI_F32: return launch_mode<EPI_F32, CG>(wres, ah, al, wh, wl, o0, o1, o2, kp, grid, smem, st);
+        case EPI_GELU_SPLIT: return launch_mode<EPI_GELU_SPLIT, CG>(wres, ah, al, wh, wl, o0, o1, o2, kp, grid, smem, st);
+        case EPI_RESID: return launch_mode<EPI_RESID, CG>(wres, ah, al, wh, wl, o0, o1, o2, kp, grid, smem, st);
+        case EPI_PLANES: return launch_mode<EPI_PLANES, CG>(wres, ah, al, wh, wl, o0, o1, o2, kp, grid, smem, st);
+        case EPI_RESID_LN: return launch_mode<EPI_RESID_LN, CG>(wres, ah, al, wh, wl, o0, o1, o2, kp, grid, smem, st);
     }
     set_last_error("gemm: bad epilogue %d", g.epilogue);
     return -1;
@@ -584,6 +833,8 @@ int gemm_pick_block_n(int N) {
         if (N % bn == 0) return bn;
     return 0;
 }
+
+bool gemm_can_fuse_ln(int N) { return N % 32 == 0 && N <= 256 && gemm_pick_block_n(N) == N; }
 
 int gemm_init() {
     if (g_encode) return 0;

@@ -96,7 +96,20 @@ struct AttnPlanes {
 };
 inline int attn_head_store(int hd) { return (hd + 15) / 16 * 16; }
 
-enum GemmEpilogue { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_RESID = 2, EPI_PLANES = 3 };
+enum GemmEpilogue { EPI_F32 = 0, EPI_GELU_SPLIT = 1, EPI_RESID = 2, EPI_PLANES = 3, EPI_RESID_LN = 4 };
+
+// EPI_RESID_LN: x <- x + A W^T + bias, fused with the LayerNorm(s) that follow (see gemm_tcgen05.cu).
+//   g0 == nullptr:  x <- v;                               out_hi/lo = LN(v; g1, b1, eps1)
+//   g0 != nullptr:  x <- y = LN(v; g0, b0, eps0) [+ add_f[f]];   out_hi/lo = LN(y; g1, b1, eps1)
+// Requires the whole row in one tile (N <= 256, N % 32 == 0).
+struct GemmLnFuse {
+    const float* x = nullptr;            // [M,N] residual stream (read here; written through GemmArgs::out_f32 == x)
+    const float *g0 = nullptr, *b0 = nullptr;
+    const float* add_f = nullptr;        // [F,N], row f = (m / J) % F
+    const float *g1 = nullptr, *b1 = nullptr;
+    float eps0 = 1e-6f, eps1 = 1e-6f;
+    int J = 1, F = 1;
+};
 
 struct GemmArgs {
     const op_t *a_hi, *a_lo;   // [M,K]
@@ -110,6 +123,7 @@ struct GemmArgs {
     float out_scale = WEIGHT_UNSCALE;   // accumulator scale applied before the bias (weights are stored pre-scaled)
     // EPI_PLANES: N = 24*hds output columns in plane order (column n -> plane n / hds, d = n % hds)
     AttnPlanes planes = {nullptr, nullptr, 0, 0};
+    GemmLnFuse ln;                      // EPI_RESID_LN
 };
 
 int launch_split_weights(const float* w, op_t* hi, op_t* lo, size_t n, cudaStream_t st);
@@ -137,6 +151,7 @@ int gemm_init();                                            // resolves cuTensor
 int launch_gemm_tcgen05(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);   // debug reference (CUDA cores)
 int gemm_pick_block_n(int N);
+bool gemm_can_fuse_ln(int N);                               // EPI_RESID_LN needs the row in one tile
 void gemm_set_cta_group(int cg);                            // 1: lone CTAs, 2 (default): tcgen05 CTA pairs
 void gemm_set_weight_stationary(int on);                    // 1 (default): keep the W slice of an n tile in shared memory when it fits
 

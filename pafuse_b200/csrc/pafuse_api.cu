@@ -4,6 +4,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -102,6 +103,7 @@ struct pafuse_ctx {
     bool committed = false;
     bool debug_simt = false;
     bool debug_simt_attn = false;
+    bool fuse_ln = true;             // LayerNorms fused into the proj / fc2 GEMM epilogues where the row fits one tile
     Profiler prof;
 };
 
@@ -275,22 +277,26 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
                 if (int rc = launch_embed(e, st)) return rc;
             }
 
-            for (int blk = 0; blk < 2 * cfg.depth; ++blk) {
+            // Parts whose rows fit one GEMM tile (C <= 256: face, hands) run proj and fc2 with the LayerNorms that
+            // follow them fused into the epilogue (EPI_RESID_LN); the others keep the separate ln_chain launches.
+            const bool fuse = ctx->fuse_ln && !ctx->debug_simt && gemm_can_fuse_ln(C);
+            const int nblk = 2 * cfg.depth;
+            for (int blk = 0; blk < nblk; ++blk) {
                 const bool temporal = blk & 1;
                 const std::string b = std::string(temporal ? "TTEblocks." : "STEblocks.") + std::to_string(blk / 2) + ".";
-                // shared norm of the previous block (+ Temporal_pos_embed before TTE 0), then norm1 -> hi/lo
                 LnParams l;
                 l.M = M; l.C = C; l.J = J; l.F = F; l.x = w.x;
-                l.g0 = l.b0 = nullptr; l.add_f = nullptr; l.eps0 = 1e-6f;
-                if (blk > 0) {
-                    const char* sn = temporal ? "Spatial_norm" : "Temporal_norm";   // norm that closed the previous block
-                    l.g0 = p.w(std::string(sn) + ".weight");
-                    l.b0 = p.w(std::string(sn) + ".bias");
-                    if (blk == 1) l.add_f = p.w("Temporal_pos_embed");
-                }
-                l.g1 = p.w(b + "norm1.weight"); l.b1 = p.w(b + "norm1.bias"); l.eps1 = 1e-6f;
+                l.g0 = l.b0 = nullptr; l.add_f = nullptr; l.eps0 = 1e-6f; l.eps1 = 1e-6f;
                 l.out_hi = w.a_hi; l.out_lo = w.a_lo;
-                {
+                if (!fuse || blk == 0) {
+                    // shared norm of the previous block (+ Temporal_pos_embed before TTE 0), then norm1 -> hi/lo
+                    if (blk > 0) {
+                        const char* sn = temporal ? "Spatial_norm" : "Temporal_norm";   // norm that closed the previous block
+                        l.g0 = p.w(std::string(sn) + ".weight");
+                        l.b0 = p.w(std::string(sn) + ".bias");
+                        if (blk == 1) l.add_f = p.w("Temporal_pos_embed");
+                    }
+                    l.g1 = p.w(b + "norm1.weight"); l.b1 = p.w(b + "norm1.bias");
                     ProfScope ps(ctx, CAT_LN, (blk > 0 ? 12.0 : 8.0) * (double)M * C, st);
                     if (int rc = launch_ln_chain(l, st)) return rc;
                 }
@@ -335,19 +341,30 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
                     if (int rc = launch_attention_tc(pl, w.o_hi, w.o_lo, Sc, F, J, C, temporal ? 1 : 0, st)) return rc;
                 }
 
+                // proj: x += o W^T + b, then norm2 -> hi/lo
+                g = GemmArgs();
+                g.M = M;
                 g.a_hi = w.o_hi; g.a_lo = w.o_lo;
                 g.w_hi = p.wh(b + "attn.proj.weight"); g.w_lo = p.wl(b + "attn.proj.weight");
                 g.bias = p.w(b + "attn.proj.bias");
                 g.out_f32 = w.x; g.N = C; g.K = C; g.epilogue = EPI_RESID;
+                if (fuse) {
+                    g.epilogue = EPI_RESID_LN;
+                    g.out_hi = w.a_hi; g.out_lo = w.a_lo;
+                    g.ln.x = w.x;
+                    g.ln.g1 = p.w(b + "norm2.weight"); g.ln.b1 = p.w(b + "norm2.bias"); g.ln.eps1 = 1e-6f;
+                    g.ln.J = J; g.ln.F = F;
+                }
                 if (int rc = run_gemm(ctx, g, st)) return rc;
-
-                l.g0 = l.b0 = nullptr; l.add_f = nullptr;
-                l.g1 = p.w(b + "norm2.weight"); l.b1 = p.w(b + "norm2.bias");
-                {
+                if (!fuse) {
+                    l.g0 = l.b0 = nullptr; l.add_f = nullptr;
+                    l.g1 = p.w(b + "norm2.weight"); l.b1 = p.w(b + "norm2.bias");
                     ProfScope ps(ctx, CAT_LN, 8.0 * (double)M * C, st);
                     if (int rc = launch_ln_chain(l, st)) return rc;
                 }
 
+                g = GemmArgs();
+                g.M = M;
                 g.a_hi = w.a_hi; g.a_lo = w.a_lo;
                 g.w_hi = p.wh(b + "mlp.fc1.weight"); g.w_lo = p.wl(b + "mlp.fc1.weight");
                 g.bias = p.w(b + "mlp.fc1.bias");
@@ -355,11 +372,27 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
                 g.N = 2 * C; g.K = C; g.epilogue = EPI_GELU_SPLIT;
                 if (int rc = run_gemm(ctx, g, st)) return rc;
 
+                // fc2: x += h W^T + b; fused: the norm that closes this block (+ Temporal_pos_embed after STE 0) and
+                // norm1 of the next block
+                g = GemmArgs();
+                g.M = M;
                 g.a_hi = w.h_hi; g.a_lo = w.h_lo;
                 g.w_hi = p.wh(b + "mlp.fc2.weight"); g.w_lo = p.wl(b + "mlp.fc2.weight");
                 g.bias = p.w(b + "mlp.fc2.bias");
                 g.out_f32 = w.x; g.out_hi = g.out_lo = nullptr;
                 g.N = C; g.K = 2 * C; g.epilogue = EPI_RESID;
+                if (fuse && blk + 1 < nblk) {
+                    const bool tnext = (blk + 1) & 1;
+                    const std::string bn = std::string(tnext ? "TTEblocks." : "STEblocks.") + std::to_string((blk + 1) / 2) + ".";
+                    const char* sn = temporal ? "Temporal_norm" : "Spatial_norm";       // norm that closes this block
+                    g.epilogue = EPI_RESID_LN;
+                    g.out_hi = w.a_hi; g.out_lo = w.a_lo;
+                    g.ln.x = w.x;
+                    g.ln.g0 = p.w(std::string(sn) + ".weight"); g.ln.b0 = p.w(std::string(sn) + ".bias"); g.ln.eps0 = 1e-6f;
+                    if (blk == 0) g.ln.add_f = p.w("Temporal_pos_embed");
+                    g.ln.g1 = p.w(bn + "norm1.weight"); g.ln.b1 = p.w(bn + "norm1.bias"); g.ln.eps1 = 1e-6f;
+                    g.ln.J = J; g.ln.F = F;
+                }
                 if (int rc = run_gemm(ctx, g, st)) return rc;
             }
 
@@ -443,6 +476,7 @@ int pafuse_create(const pafuse_config* cfg, pafuse_ctx** out) {
     PAFUSE_CUDA_OK(cudaMemcpy(ctx->flip_perm_dev, cfg->flip_perm, cfg->num_kps * sizeof(int), cudaMemcpyHostToDevice));
     ctx->cfg.flip_perm = nullptr;
     if (int rc = gemm_init()) return rc;
+    if (const char* e = getenv("PAFUSE_FUSE_LN")) ctx->fuse_ln = atoi(e) != 0;
     *out = ctx;
     return 0;
 }
@@ -637,6 +671,12 @@ int pafuse_set_gemm_cta_group(int32_t cta_group) {
     }
     if (int rc = gemm_init()) return rc;
     gemm_set_cta_group(cta_group);
+    return 0;
+}
+
+int pafuse_set_fuse_layernorm(pafuse_ctx* ctx, int32_t enable) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    ctx->fuse_ln = enable != 0;
     return 0;
 }
 

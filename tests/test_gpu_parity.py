@@ -162,6 +162,20 @@ def test_tensor_core_gemm_equals_cuda_core_gemm_on_the_whole_model():
     assert (a - b).abs().max().item() < 3e-5
 
 
+def test_layernorm_fused_in_gemm_epilogue_equals_separate_launches():
+    """proj / fc2 with the following LayerNorms in their epilogue (face, hands) against the ln_chain launches."""
+    from pafuse_testlib import build_case
+    c = build_case("small_B2_H2_K3")
+    fused = _model(c)
+    plain = _model(c)
+    plain.native_context().set_fuse_layernorm(False)
+    a = fused(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
+    b = plain(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
+    assert (a - b).abs().max().item() < 2e-5
+    _check_pose(a, c["golden"]["out"])
+    _check_pose(b, c["golden"]["out"])
+
+
 @pytest.mark.parametrize("max_seqs", [1, 3])
 def test_workspace_chunking_is_invisible(max_seqs):
     """max_seqs smaller than the sequence count must not change the result.  Rows are independent, but the
