@@ -42,6 +42,7 @@ constexpr int UK = 16;               // K per tcgen05.mma (16-bit operands)
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_SLACK = 1024 + 512;              // alignment of the dynamic window + the static barriers
+constexpr int SMEM_SLACK_LN = 1024 + 512 + 1024;    // + the row-sum exchange buffer of EPI_RESID_LN
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 8;
@@ -696,7 +697,10 @@ int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
     auto kern = gemm_f16x3_kernel<EPI, CG, WRES>;
     static bool configured = false;                                   // per template instance
     if (!configured) {
-        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 512));
+        cudaFuncAttributes fa;
+        PAFUSE_CUDA_OK(cudaFuncGetAttributes(&fa, kern));              // static shared memory counts against the 227 KiB
+        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            SMEM_LIMIT - (int)fa.sharedSizeBytes));
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -752,6 +756,7 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     }
     const int max_groups = g_num_sms / CG;
     const int WN = BN / CG;
+    const int slack = g.epilogue == EPI_RESID_LN ? SMEM_SLACK_LN : SMEM_SLACK;
 
     // Weight-stationary mode: the W slice of one n tile (all of K, hi and lo) stays in shared memory and only A
     // is streamed, in 32-wide K stages.  Chosen when the slice leaves room for >= 3 stages; the K = 2C layers
@@ -763,7 +768,7 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     if (g_wres_enabled && g.K % 32 == 0 && kp.n_tiles <= max_groups) {
         const int w_res = ((g.K + BKW - 1) / BKW) * 2 * WN * BKW * 2;
         const int a_stage = 2 * BM * 32 * 2;
-        const int stages = (SMEM_LIMIT - SMEM_SLACK - STG_BYTES - w_res) / a_stage;
+        const int stages = (SMEM_LIMIT - slack - STG_BYTES - w_res) / a_stage;
         if (stages >= g_wres_min_stages) {
             wres = true;
             kp.a_bk = 32;
@@ -776,7 +781,7 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     }
     if (!wres) {
         kp.stage_bytes = 2 * BM * BKW * 2 + 2 * WN * BKW * 2;
-        int stages = (SMEM_LIMIT - SMEM_SLACK - STG_BYTES) / kp.stage_bytes;
+        int stages = (SMEM_LIMIT - slack - STG_BYTES) / kp.stage_bytes;
         kp.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     }
 
