@@ -138,6 +138,26 @@ __device__ __forceinline__ void ln_fetch_x(const KernelParams& p, float4 (&xr)[8
     }
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// 32 consecutive floats of a per-column parameter vector, the same for every lane (broadcast loads).  Issued as one
+// batch ahead of their use: loaded one by one next to the FMAs they feed, every load's latency was exposed
+// (profiles/r1j_*: a quarter of the epilogue time).
+__device__ __forceinline__ void load_vec32(float4 (&v)[8], const float* src) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(s4 + i);
+}
+
 template <int CG>
 __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const CUtensorMap& tm_x, const CUtensorMap& tm_hi,
                                                   const CUtensorMap& tm_lo, uint8_t* box, float* xch, uint32_t t_base,
@@ -150,10 +170,10 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
     const float invN = 1.0f / (float)N;
     float* my_x = xch + (q * 32 + lane) * 2;
     const int bar_id = 1 + q;
-    uint8_t* rowp = box + lane * 128;
+    const uint32_t box_s = smem_u32(box);
+    const uint32_t row_s = box_s + lane * 128;                        // this lane's row of a 32 x 128 B box
     const int sw = lane & 7;
 
-    auto fetch_x = [&](int c0) { ln_fetch_x(p, xr, row0, c0, lane); };
     auto exchange = [&](float v) -> float {                           // sum over the two warps that share this row
         my_x[half] = v;
         pair_bar_sync(bar_id);
@@ -162,18 +182,19 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         return v + o;
     };
     auto stats = [&](float mean, float eps) -> float {                // second pass: 1 / sqrt(var + eps)
-        float sq = 0.f;
+        float sq0 = 0.f, sq1 = 0.f;
         for (int ci = 0; ci < nchunks; ++ci) {
             uint32_t r[32];
             tmem_ld_32x32(t_base + (uint32_t)((half + 2 * ci) * 32), r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float d = __uint_as_float(r[i]) - mean;
-                sq = fmaf(d, d, sq);
+            for (int i = 0; i < 32; i += 2) {
+                const float d0 = __uint_as_float(r[i]) - mean, d1 = __uint_as_float(r[i + 1]) - mean;
+                sq0 = fmaf(d0, d0, sq0);
+                sq1 = fmaf(d1, d1, sq1);
             }
         }
-        return 1.0f / sqrtf(exchange(sq) * invN + eps);
+        return 1.0f / sqrtf(exchange(sq0 + sq1) * invN + eps);
     };
     // LN(v; g, b) of the row values held in tensor memory -> fp16 hi/lo boxes -> TMA stores
     auto emit_split = [&](float mean, float rstd, const float* g, const float* b) {
@@ -181,33 +202,28 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         for (int ci = 0; ci < nchunks; ++ci) {
             const int c0 = (half + 2 * ci) * 32;
             uint32_t r[32];
+            float4 gv[8], bv[8];
             tmem_ld_32x32(t_base + (uint32_t)c0, r);
-            if (lane == 0) bulk_wait_group_read<0>();
+            load_vec32(gv, g + c0);
+            load_vec32(bv, b + c0);
             tmem_ld_wait();
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float v0 = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), rstd, mr), gv[i].x, bv[i].x);
+                const float v1 = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), rstd, mr), gv[i].y, bv[i].y);
+                const float v2 = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), rstd, mr), gv[i].z, bv[i].z);
+                const float v3 = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), rstd, mr), gv[i].w, bv[i].w);
+                split_pair_sat(v0, v1, hi[2 * i], lo[2 * i]);
+                split_pair_sat(v2, v3, hi[2 * i + 1], lo[2 * i + 1]);
+            }
+            if (lane == 0) bulk_wait_group_read<0>();                 // the store that last used the box has read it
             __syncwarp();
-            const float4* g4 = reinterpret_cast<const float4*>(g + c0);
-            const float4* b4 = reinterpret_cast<const float4*>(b + c0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 ga = __ldg(g4 + 2 * i), gb = __ldg(g4 + 2 * i + 1);
-                const float4 ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
-                float v[8];
-                v[0] = fmaf(fmaf(__uint_as_float(r[8 * i + 0]), rstd, mr), ga.x, ba.x);
-                v[1] = fmaf(fmaf(__uint_as_float(r[8 * i + 1]), rstd, mr), ga.y, ba.y);
-                v[2] = fmaf(fmaf(__uint_as_float(r[8 * i + 2]), rstd, mr), ga.z, ba.z);
-                v[3] = fmaf(fmaf(__uint_as_float(r[8 * i + 3]), rstd, mr), ga.w, ba.w);
-                v[4] = fmaf(fmaf(__uint_as_float(r[8 * i + 4]), rstd, mr), gb.x, bb.x);
-                v[5] = fmaf(fmaf(__uint_as_float(r[8 * i + 5]), rstd, mr), gb.y, bb.y);
-                v[6] = fmaf(fmaf(__uint_as_float(r[8 * i + 6]), rstd, mr), gb.z, bb.z);
-                v[7] = fmaf(fmaf(__uint_as_float(r[8 * i + 7]), rstd, mr), gb.w, bb.w);
-                uint2 h0, l0, h1, l1;
-                split_pair_sat(v[0], v[1], h0.x, l0.x);
-                split_pair_sat(v[2], v[3], h0.y, l0.y);
-                split_pair_sat(v[4], v[5], h1.x, l1.x);
-                split_pair_sat(v[6], v[7], h1.y, l1.y);
-                const int off = lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);   // 32 rows x 64 B, 64-byte swizzle
-                *reinterpret_cast<uint4*>(box + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                *reinterpret_cast<uint4*>(box + 2048 + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                const uint32_t off = (uint32_t)(lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4));   // 32 rows x 64 B, 64-byte swizzle
+                sts128u(box_s + off, make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]));
+                sts128u(box_s + 2048 + off, make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]));
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -224,34 +240,34 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
     for (int ci = 0; ci < nchunks; ++ci) {
         const int c0 = (half + 2 * ci) * 32;
         uint32_t r[32];
+        float4 bv[8];
         tmem_ld_32x32(t_base + (uint32_t)c0, r);
+        load_vec32(bv, p.bias + c0);
         if (lane == 0) bulk_wait_group_read<0>();                     // the store that last used the box has read it
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {                                 // transpose through the box (128-byte swizzle)
+        for (int i = 0; i < 8; ++i) {                                 // transpose x through the box (128-byte swizzle)
             const int rr = (lane >> 3) + 4 * i;
-            *reinterpret_cast<float4*>(box + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)) = xr[i];
+            sts128(box_s + (uint32_t)(rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)), xr[i]);
         }
         __syncwarp();
-        if (ci + 1 < nchunks) fetch_x(c0 + 64);                       // next chunk's x, in flight during the math
+        if (ci + 1 < nchunks) ln_fetch_x(p, xr, row0, c0 + 64, lane);  // next chunk's x, in flight during the math
         tmem_ld_wait();
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + c0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float4* slot = reinterpret_cast<float4*>(rowp + ((i ^ sw) << 4));
-            const float4 xv = *slot;
-            const float4 bb = __ldg(b4 + i);
+            const uint32_t slot = row_s + (uint32_t)((i ^ sw) << 4);
+            const float4 xv = lds128(slot);
             float4 v;
-            v.x = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bb.x) + xv.x;
-            v.y = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bb.y) + xv.y;
-            v.z = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bb.z) + xv.z;
-            v.w = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bb.w) + xv.w;
+            v.x = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bv[i].x) + xv.x;
+            v.y = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bv[i].y) + xv.y;
+            v.z = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bv[i].z) + xv.z;
+            v.w = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bv[i].w) + xv.w;
             sum += (v.x + v.y) + (v.z + v.w);
             r[4 * i + 0] = __float_as_uint(v.x);
             r[4 * i + 1] = __float_as_uint(v.y);
             r[4 * i + 2] = __float_as_uint(v.z);
             r[4 * i + 3] = __float_as_uint(v.w);
-            if (!chained) *slot = v;
+            if (!chained) sts128(slot, v);
         }
         tmem_st_32x32(t_base + (uint32_t)c0, r);
         if (!chained) {
@@ -276,30 +292,41 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         for (int ci = 0; ci < nchunks; ++ci) {
             const int c0 = (half + 2 * ci) * 32;
             uint32_t r[32];
+            float4 gv[8], bv[8];
             tmem_ld_32x32(t_base + (uint32_t)c0, r);
-            if (lane == 0) bulk_wait_group_read<0>();
+            load_vec32(gv, f.g0 + c0);
+            load_vec32(bv, f.b0 + c0);
             tmem_ld_wait();
-            __syncwarp();
-            const float4* g4 = reinterpret_cast<const float4*>(f.g0 + c0);
-            const float4* b4 = reinterpret_cast<const float4*>(f.b0 + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 gg = __ldg(g4 + i), bb = __ldg(b4 + i);
                 float4 y;
-                y.x = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), rstd, mr), gg.x, bb.x);
-                y.y = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), rstd, mr), gg.y, bb.y);
-                y.z = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), rstd, mr), gg.z, bb.z);
-                y.w = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), rstd, mr), gg.w, bb.w);
-                if (addr) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(addr + c0) + i);
-                    y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w;
-                }
-                sum1 += (y.x + y.y) + (y.z + y.w);
+                y.x = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), rstd, mr), gv[i].x, bv[i].x);
+                y.y = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), rstd, mr), gv[i].y, bv[i].y);
+                y.z = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), rstd, mr), gv[i].z, bv[i].z);
+                y.w = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), rstd, mr), gv[i].w, bv[i].w);
                 r[4 * i + 0] = __float_as_uint(y.x);
                 r[4 * i + 1] = __float_as_uint(y.y);
                 r[4 * i + 2] = __float_as_uint(y.z);
                 r[4 * i + 3] = __float_as_uint(y.w);
-                *reinterpret_cast<float4*>(rowp + ((i ^ sw) << 4)) = y;
+            }
+            if (addr) {                                               // Temporal_pos_embed (after STE block 0 only)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(addr + c0) + i);
+                    r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + a.x);
+                    r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + a.y);
+                    r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + a.z);
+                    r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + a.w);
+                }
+            }
+            if (lane == 0) bulk_wait_group_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 y = make_float4(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]),
+                                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                sum1 += (y.x + y.y) + (y.z + y.w);
+                sts128(row_s + (uint32_t)((i ^ sw) << 4), y);
             }
             tmem_st_32x32(t_base + (uint32_t)c0, r);
             fence_proxy_async_smem();
