@@ -125,8 +125,8 @@ __device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %
 // It replaces the L2-side reduction of EPI_RESID plus one ln_chain_kernel launch (8-12 B per element of DRAM
 // traffic).  A thread owns one row (= TMEM lane); the two warps of a lane quarter split the 32-column chunks
 // (even / odd) and exchange their partial row sums through shared memory.  The row values stay in the
-// accumulator's tensor memory between the passes (tcgen05.st / tcgen05.ld), statistics are two-pass like
-// ln_chain_kernel.  x is fetched with coalesced 16-byte loads one chunk ahead (registers), transposed through the
+// accumulator's tensor memory between the passes (tcgen05.st / tcgen05.ld); statistics are gathered in the pass
+// that produces the values (shifted sums, see merge_stats).  x is fetched with coalesced 16-byte loads one chunk ahead (registers), transposed through the
 // warp's staging box, which then carries the output row by row to the TMA store.
 // coalesced fetch of a 32 x 32 box of x: lane -> 16 bytes at column (lane & 7) * 4 of rows (lane >> 3) + 4 i
 __device__ __forceinline__ void ln_fetch_x(const KernelParams& p, float4 (&xr)[8], int row0, int c0, int lane) {
@@ -174,27 +174,26 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
     const uint32_t row_s = box_s + lane * 128;                        // this lane's row of a 32 x 128 B box
     const int sw = lane & 7;
 
-    auto exchange = [&](float v) -> float {                           // sum over the two warps that share this row
+    auto partner = [&](float v) -> float {                            // value of the warp that shares this row
         my_x[half] = v;
         pair_bar_sync(bar_id);
         const float o = my_x[half ^ 1];
         pair_bar_sync(bar_id);                                        // the slot may be rewritten after this point
-        return v + o;
+        return o;
     };
-    auto stats = [&](float mean, float eps) -> float {                // second pass: 1 / sqrt(var + eps)
-        float sq0 = 0.f, sq1 = 0.f;
-        for (int ci = 0; ci < nchunks; ++ci) {
-            uint32_t r[32];
-            tmem_ld_32x32(t_base + (uint32_t)((half + 2 * ci) * 32), r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-                const float d0 = __uint_as_float(r[i]) - mean, d1 = __uint_as_float(r[i + 1]) - mean;
-                sq0 = fmaf(d0, d0, sq0);
-                sq1 = fmaf(d1, d1, sq1);
-            }
-        }
-        return 1.0f / sqrtf(exchange(sq0 + sq1) * invN + eps);
+    // Row statistics in ONE pass over the values (a second tensor-memory pass per norm cost 40 % of the epilogue):
+    // each warp accumulates S = sum(v - K), Q = sum((v - K)^2) around K = its first value of the row, which keeps
+    // Q - S^2/n free of cancellation; the two warps' (mean, M2) are merged with the pairwise update of Chan et al.
+    const float na = (float)(nchunks * 32), nb = (float)N - na;
+    auto merge_stats = [&](float K, float S, float Q, float eps, float& mean, float& rstd) {
+        const float mean_a = na > 0.f ? K + S / na : 0.f;               // a 32-column row leaves the odd warp empty
+        const float m2_a = na > 0.f ? Q - S * S / na : 0.f;
+        const float mean_b = partner(mean_a);
+        const float m2_b = partner(m2_a);
+        const float delta = mean_b - mean_a;
+        mean = mean_a + delta * (nb * invN);
+        const float m2 = m2_a + m2_b + delta * delta * (na * nb * invN);
+        rstd = 1.0f / sqrtf(m2 * invN + eps);
     };
     // LN(v; g, b) of the row values held in tensor memory -> fp16 hi/lo boxes -> TMA stores
     auto emit_split = [&](float mean, float rstd, const float* g, const float* b) {
@@ -236,7 +235,7 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
     };
 
     // ---- pass 1: v = x + acc * scale + bias -> tensor memory (and, when not chained, -> x)
-    float sum = 0.f;
+    float K = 0.f, S = 0.f, Q = 0.f;
     for (int ci = 0; ci < nchunks; ++ci) {
         const int c0 = (half + 2 * ci) * 32;
         uint32_t r[32];
@@ -262,7 +261,12 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
             v.y = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bv[i].y) + xv.y;
             v.z = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bv[i].z) + xv.z;
             v.w = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bv[i].w) + xv.w;
-            sum += (v.x + v.y) + (v.z + v.w);
+            if (ci == 0 && i == 0) K = v.x;
+            {
+                const float d0 = v.x - K, d1 = v.y - K, d2 = v.z - K, d3 = v.w - K;
+                S += (d0 + d1) + (d2 + d3);
+                Q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, Q))));
+            }
             r[4 * i + 0] = __float_as_uint(v.x);
             r[4 * i + 1] = __float_as_uint(v.y);
             r[4 * i + 2] = __float_as_uint(v.z);
@@ -280,15 +284,15 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         }
     }
     tmem_st_wait_all();
-    float mean = exchange(sum) * invN;
-    float rstd = stats(mean, chained ? f.eps0 : f.eps1);
+    float mean, rstd;
+    merge_stats(K, S, Q, chained ? f.eps0 : f.eps1, mean, rstd);
 
     if (chained) {
         // ---- y = LN(v; g0, b0) [+ add_f[f]] -> x and tensor memory
         const float mr = -mean * rstd;
         const long long row = (long long)row0 + lane;
         const float* addr = f.add_f ? f.add_f + (size_t)((row / f.J) % f.F) * N : nullptr;
-        float sum1 = 0.f;
+        K = 0.f; S = 0.f; Q = 0.f;
         for (int ci = 0; ci < nchunks; ++ci) {
             const int c0 = (half + 2 * ci) * 32;
             uint32_t r[32];
@@ -325,7 +329,10 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
             for (int i = 0; i < 8; ++i) {
                 float4 y = make_float4(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]),
                                        __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                sum1 += (y.x + y.y) + (y.z + y.w);
+                if (ci == 0 && i == 0) K = y.x;
+                const float d0 = y.x - K, d1 = y.y - K, d2 = y.z - K, d3 = y.w - K;
+                S += (d0 + d1) + (d2 + d3);
+                Q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, Q))));
                 sts128(row_s + (uint32_t)((i ^ sw) << 4), y);
             }
             tmem_st_32x32(t_base + (uint32_t)c0, r);
@@ -337,8 +344,7 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
             }
         }
         tmem_st_wait_all();
-        mean = exchange(sum1) * invN;
-        rstd = stats(mean, f.eps1);
+        merge_stats(K, S, Q, f.eps1, mean, rstd);
     }
     emit_split(mean, rstd, f.g1, f.b1);
 
