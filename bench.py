@@ -184,6 +184,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     H, K, Bl = args.proposals, args.timesteps, args.clips
     B = Bl * world
@@ -191,6 +192,8 @@ def run_ours(args):
     model = pafuse_b200.D3DP(synthetic.default_args(depth=8), sk.joints_left, sk.joints_right, sk, is_train=False,
                              num_proposals=H, sampling_timesteps=K)
     model.load_state_dict(synthetic.synthetic_state_dict(seed=1, depth=8), strict=False)
+    if args.max_seqs > 0:
+        model.max_seqs = args.max_seqs
     model = model.to(dev).eval()
     engine = pd.CudaEngine(model, sk)
     x2d_h, x2df_h = synthetic.synthetic_inputs(B, seed=1)
@@ -319,6 +322,7 @@ def main():
     ap.add_argument("--timesteps", type=int, default=5)
     ap.add_argument("--cpu-clips", type=int, default=1, help="clips in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-seqs", type=int, default=0, help="sequences per workspace pass (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
