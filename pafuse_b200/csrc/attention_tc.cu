@@ -67,6 +67,7 @@ struct AttnTcParams {
     int rows_per_iter;        // 32 / chunks_per_row: staging rows one copy-out instruction of a warp covers
     // tensor-memory columns: S / P of stage s at tm_s0 + s * tm_stride_s (+ tm_phi_off / tm_plo_off), O at tm_o0 + s * tm_stride_o
     int tm_s0, tm_stride_s, tm_phi_off, tm_plo_off, tm_o0, tm_stride_o;
+    int n_acc;                // O accumulators per stage (HDP columns each): the three f16x3 passes of PV go to different ones
     op_t* o_hi;
     op_t* o_lo;
 };
@@ -248,6 +249,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
             const uint32_t d_s = tmem_base + (uint32_t)(p.tm_s0 + stage * p.tm_stride_s);
             const uint32_t d_o = tmem_base + (uint32_t)(p.tm_o0 + stage * p.tm_stride_o);
+            // n_acc = 3: the passes go to accumulators 0, 1, 2; n_acc = 2: lo*hi and hi*hi -> 0, hi*lo -> 1; n_acc = 1: all -> 0
+            const uint32_t d_o1 = p.n_acc >= 2 ? d_o + (uint32_t)HDP : d_o;
+            const uint32_t d_o2 = p.n_acc >= 3 ? d_o + 2u * (uint32_t)HDP : d_o;
             const uint32_t d_phi = d_s + (uint32_t)p.tm_phi_off, d_plo = d_s + (uint32_t)p.tm_plo_off;
             auto issue_qk = [&](int it) {
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
@@ -283,9 +287,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     const uint64_t vl = make_desc(sa + 5 * TILE_BYTES + vo, SBO, LAYOUT);
                     const uint32_t ph_a = d_phi + (uint32_t)k * 8u;               // 16 fp16 keys = 8 columns
                     const uint32_t pl_a = d_plo + (uint32_t)k * 8u;
-                    umma_f16_ts(d_o, pl_a, vh, idesc_pv, k != 0 ? 1u : 0u);
-                    umma_f16_ts(d_o, ph_a, vl, idesc_pv, 1u);
-                    umma_f16_ts(d_o, ph_a, vh, idesc_pv, 1u);
+                    // Separate accumulators per pass: the PV MMAs are tiny (N = HDP) and a chain of 3 * key_steps
+                    // dependent accumulations into ONE tile ran at the pipe's latency, ~90 cycles per MMA
+                    // (profiles/r1m_*: every attention variant cost ~90-110 cycles per issued MMA).
+                    const uint32_t first = k != 0 ? 1u : 0u;
+                    umma_f16_ts(d_o, pl_a, vh, idesc_pv, first);
+                    umma_f16_ts(d_o1, ph_a, vl, idesc_pv, p.n_acc >= 2 ? first : 1u);
+                    umma_f16_ts(d_o2, ph_a, vh, idesc_pv, p.n_acc >= 3 ? first : 1u);
                 }
                 umma_commit<1>(&v_empty[stage]);
                 umma_commit<1>(&o_full[stage]);
@@ -409,6 +417,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             if (warp_live) {
                 tmem_ld_32x32(o_addr, ov);
                 if (HDP == 64) tmem_ld_32x32(o_addr + 32u, ov + 32);
+                for (int a = 1; a < p.n_acc; ++a) {            // add the other passes' accumulators
+                    uint32_t oa[HDP];
+                    tmem_ld_32x32(o_addr + (uint32_t)(a * HDP), oa);
+                    if (HDP == 64) tmem_ld_32x32(o_addr + (uint32_t)(a * HDP) + 32u, oa + 32);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < HDP; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) + __uint_as_float(oa[i]));
+                }
                 tmem_ld_wait();
             }
             tcgen05_fence_before();
@@ -499,6 +515,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
 PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
 int g_sms = 0;
+int g_n_acc_cap = 3;     // PAFUSE_ATT_NACC: cap on the O accumulators per stage (1 = one dependent chain, as before)
 int g_sep_mode = 1;      // PAFUSE_ATT_SEP: 0 aliased layout only, 1 separate when it fits (default), 2 also with one group less per tile (slower: measured)
 
 int att_init() {
@@ -515,6 +532,7 @@ int att_init() {
     PAFUSE_CUDA_OK(cudaGetDevice(&dev));
     PAFUSE_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("PAFUSE_ATT_SEP")) g_sep_mode = atoi(e);
+    if (const char* e = getenv("PAFUSE_ATT_NACC")) g_n_acc_cap = atoi(e);
     return 0;
 }
 
@@ -599,9 +617,11 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
             if (hdp + s_cols + 2 * p_half <= 256) {
                 sep = true;
                 p.G = G;
+                p.n_acc = (256 - s_cols - 2 * p_half) / hdp;
+                if (p.n_acc > 3) p.n_acc = 3;
                 p.tm_o0 = 0;
                 p.tm_stride_o = 256;
-                p.tm_s0 = hdp;
+                p.tm_s0 = p.n_acc * hdp;
                 p.tm_stride_s = 256;
                 p.tm_phi_off = s_cols;
                 p.tm_plo_off = s_cols + p_half;
@@ -614,9 +634,11 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
         p.tm_stride_s = 128;
         p.tm_phi_off = 0;
         p.tm_plo_off = 64;
+        p.n_acc = hdp == 32 ? 3 : 2;                               // 256 columns are left for O: 2 stages x n_acc x hdp
         p.tm_o0 = 256;
-        p.tm_stride_o = 64;
+        p.tm_stride_o = p.n_acc * hdp;
     }
+    if (p.n_acc > g_n_acc_cap) p.n_acc = g_n_acc_cap < 1 ? 1 : g_n_acc_cap;
     p.hd = hd;
     p.C = C;
     p.J = J;
