@@ -149,7 +149,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     __shared__ uint32_t tmem_base_slot;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler: role code uses the uniform datapath
     const int lane = threadIdx.x & 31;
     const int L = LT ? LT : p.L;
     const int Lp = LT ? NCH_MAX * 32 : p.Lp;
@@ -253,6 +253,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             const uint32_t d_o1 = p.n_acc >= 2 ? d_o + (uint32_t)HDP : d_o;
             const uint32_t d_o2 = p.n_acc >= 3 ? d_o + 2u * (uint32_t)HDP : d_o;
             const uint32_t d_phi = d_s + (uint32_t)p.tm_phi_off, d_plo = d_s + (uint32_t)p.tm_plo_off;
+            // Operand descriptors of this stage are loop invariants; only their 16-byte address field moves.  Built
+            // inside the loops they made the single issuing thread the bottleneck of every attention variant:
+            // ~90-110 cycles per issued MMA whatever its shape (profiles/r1m_*, r1p_*).
+            const uint64_t qh0 = make_desc(sa, SBO, LAYOUT), ql0 = make_desc(sa + TILE_BYTES, SBO, LAYOUT);
+            const uint64_t kh0 = make_desc(sa + 2 * TILE_BYTES, SBO, LAYOUT), kl0 = make_desc(sa + 3 * TILE_BYTES, SBO, LAYOUT);
+            const uint64_t vh0 = make_desc(sa + 4 * TILE_BYTES, SBO, LAYOUT), vl0 = make_desc(sa + 5 * TILE_BYTES, SBO, LAYOUT);
+            constexpr uint64_t V_STEP = (16u * ROWB) >> 4;
             auto issue_qk = [&](int it) {
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(&qk_full[stage], ph);
@@ -262,13 +269,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 // before this point and the tensor pipe executes in issue order
 #pragma unroll
                 for (int k = 0; k < HDP / 16; ++k) {
-                    const uint32_t ko = (uint32_t)k * 32u;
-                    const uint64_t qh = make_desc(sa + ko, SBO, LAYOUT), ql = make_desc(sa + TILE_BYTES + ko, SBO, LAYOUT);
-                    const uint64_t kh = make_desc(sa + 2 * TILE_BYTES + ko, SBO, LAYOUT);
-                    const uint64_t kl = make_desc(sa + 3 * TILE_BYTES + ko, SBO, LAYOUT);
-                    umma_f16_ss<1>(d_s, ql, kh, idesc_qk, k != 0 ? 1u : 0u);
-                    umma_f16_ss<1>(d_s, qh, kl, idesc_qk, 1u);
-                    umma_f16_ss<1>(d_s, qh, kh, idesc_qk, 1u);
+                    const uint64_t ko = (uint64_t)(k * 2);     // 32 bytes along the row, in 16-byte descriptor units
+                    umma_f16_ss<1>(d_s, ql0 + ko, kh0 + ko, idesc_qk, k != 0 ? 1u : 0u);
+                    umma_f16_ss<1>(d_s, qh0 + ko, kl0 + ko, idesc_qk, 1u);
+                    umma_f16_ss<1>(d_s, qh0 + ko, kh0 + ko, idesc_qk, 1u);
                 }
                 umma_commit<1>(&qk_empty[stage]);              // Q,K tiles of this stage may be overwritten
                 umma_commit<1>(&s_full[stage]);
@@ -281,12 +285,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 mbar_wait(&o_empty[stage], ph ^ 1);            // the softmax group has read O of unit it-2
                 mbar_wait(&p_full[stage], ph);                 // P of this unit is in tensor memory
                 tcgen05_fence_after();
-                for (int k = 0; k < key_steps; ++k) {
-                    const uint32_t vo = (uint32_t)k * 16u * ROWB;                 // 16 keys further down the V tile
-                    const uint64_t vh = make_desc(sa + 4 * TILE_BYTES + vo, SBO, LAYOUT);
-                    const uint64_t vl = make_desc(sa + 5 * TILE_BYTES + vo, SBO, LAYOUT);
-                    const uint32_t ph_a = d_phi + (uint32_t)k * 8u;               // 16 fp16 keys = 8 columns
-                    const uint32_t pl_a = d_plo + (uint32_t)k * 8u;
+                uint64_t vh = vh0, vl = vl0;
+                uint32_t ph_a = d_phi, pl_a = d_plo;
+                for (int k = 0; k < key_steps; ++k, vh += V_STEP, vl += V_STEP, ph_a += 8u, pl_a += 8u) {
+                    // 16 keys further down the V tile / 16 fp16 keys = 8 tensor-memory columns further in P
                     // Separate accumulators per pass: the PV MMAs are tiny (N = HDP) and a chain of 3 * key_steps
                     // dependent accumulations into ONE tile ran at the pipe's latency, ~90 cycles per MMA
                     // (profiles/r1m_*: every attention variant cost ~90-110 cycles per issued MMA).

@@ -378,7 +378,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     uint8_t* smem_st = smem + (WRES ? p.w_res_bytes : 0);     // operand stage ring
     uint8_t* smem_box = smem_st + (size_t)p.stages * p.stage_bytes;
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler: role code uses the uniform datapath
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
