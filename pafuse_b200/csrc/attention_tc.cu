@@ -517,7 +517,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
 PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
 int g_sms = 0;
-int g_n_acc_cap = 3;     // PAFUSE_ATT_NACC: cap on the O accumulators per stage (1 = one dependent chain, as before)
+int g_n_acc_cap = 1;     // PAFUSE_ATT_NACC: O accumulators per stage the PV passes are spread over (measured: 1 is fastest, the extra tensor-memory reads cost more than the shorter MMA chains save)
 int g_sep_mode = 1;      // PAFUSE_ATT_SEP: 0 aliased layout only, 1 separate when it fits (default), 2 also with one group less per tile (slower: measured)
 
 int att_init() {
