@@ -113,6 +113,25 @@ int pafuse_aggregate(pafuse_ctx* ctx, const float* pred, const float* traj, cons
                      const float* x2d, float* jagg, float* pagg, int32_t* select, float* reproj, int32_t B, int32_t K,
                      int32_t H, void* stream);
 
+/* ---- caller-side preparation (the code around the model call in main_h3wb.py / in_the_wild) ----
+ *
+ * pafuse_prepare_clips: eval_data_prepare (main_h3wb.py:122-154, in_the_wild/utils.py:279-320) fused with the flip-TTA
+ * input construction (main_h3wb.py:268-270, in_the_wild/utils.py:340-342).  seq [T,num_kps,2] -> clips
+ * [ceil(T/F),F,num_kps,2] (last clip = last F frames; T < F: last frame repeated) and, when clips_flip != NULL, the
+ * same clips of the flipped sequence (x negated, left/right joints swapped with the context's flip_perm). */
+int pafuse_prepare_clips(pafuse_ctx* ctx, const float* seq, int64_t T, float* clips, float* clips_flip, void* stream);
+
+/* Clips back to one sequence (in_the_wild/h3wb_diffusion.py:119-133): pred [n_clips,K,H,F,num_kps,3] ->
+ * out [K,H,T,num_kps,3]; the last T mod F frames are the last frames of the last clip. */
+int pafuse_stitch_clips(pafuse_ctx* ctx, const float* pred, int64_t n_clips, int32_t K, int32_t H, int64_t T, float* out,
+                        void* stream);
+
+/* OpenPifPaf detections to the model's 2D input (in_the_wild/h3wb_diffusion.py:64-77 + normalize_screen_coordinates,
+ * common/camera.py:7-11): raw [T,num_kps-1,3] (x, y, confidence; pixels) -> kp [T,num_kps,2]; joint 0 is the mean of
+ * joints 12 and 13. */
+int pafuse_keypoints_from_detections(pafuse_ctx* ctx, const float* raw, int64_t T, int32_t width, int32_t height, float* kp,
+                                     void* stream);
+
 /* Per-launch device timing for the roofline leg of bench.py: while enabled, every kernel this
  * context launches is bracketed by CUDA events on the launching stream.  pafuse_profile_read
  * synchronises and returns, per category (0 tensor-core GEMM, 1 attention, 2 LayerNorm chain,

@@ -325,3 +325,32 @@ def stitch_clips(pred: torch.Tensor, total_frames: int) -> torch.Tensor:
     if left > 0:
         out[:, :, -left:] = pred[-1][:, :, -left:]
     return out
+
+
+def flip_inputs_2d(x2d: torch.Tensor, kps_left, kps_right) -> torch.Tensor:
+    """Flip-TTA twin of a 2D input built by the callers: main_h3wb.py:268-270, in_the_wild/utils.py:340-342."""
+    out = x2d.clone()
+    out[..., 0] *= -1
+    out[..., list(kps_left) + list(kps_right), :] = out[..., list(kps_right) + list(kps_left), :]
+    return out
+
+
+def normalize_screen_coordinates(X, w: int, h: int):
+    """common/camera.py:7-11 on a numpy float32 array: X / w * 2 stays float32, the subtraction of the python-float
+    list promotes to float64 (that is what the reference hands to astype('float32') later)."""
+    import numpy as np
+    assert X.shape[-1] == 2
+    return X / w * 2 - np.array([1, h / w])
+
+
+def keypoints_from_openpifpaf(detections, w: int, h: int) -> torch.Tensor:
+    """in_the_wild/h3wb_diffusion.py:64-77 (+ the astype('float32') of in_the_wild/utils.py:338): detections
+    (T,133,3) pixel (x, y, confidence) -> (T,134,2) normalised input with joint 0 = mean of joints 12 and 13."""
+    import numpy as np
+    det = detections.numpy().astype(np.float32)
+    T = det.shape[0]
+    kp = np.zeros((T, det.shape[1] + 1, 2), dtype=np.float32)
+    kp[:, 1:, 0] = det[:, :, 0]
+    kp[:, 1:, 1] = det[:, :, 1]
+    kp[:, :1, :] = (kp[:, 12:13, :] + kp[:, 13:14, :]) / 2.
+    return torch.from_numpy(normalize_screen_coordinates(kp, w, h).astype("float32"))

@@ -43,6 +43,9 @@ _SIGNATURES = {
     "pafuse_project_to_2d": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "pafuse_aggregate": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "pafuse_prepare_clips": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "pafuse_stitch_clips": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
+    "pafuse_keypoints_from_detections": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "pafuse_profile_enable": (c_int32, [c_void_p, c_int32]),
     "pafuse_profile_read": (c_int32, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64), c_int32]),
     "pafuse_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
@@ -254,6 +257,36 @@ class NativeContext:
 
     def set_debug_simt_gemm(self, enable: bool):
         check(self.lib.pafuse_set_debug_simt_gemm(self.handle, 1 if enable else 0), "pafuse_set_debug_simt_gemm")
+
+    # ---- caller-side preparation
+    def prepare_clips(self, seq, want_flip=True):
+        seq = _f32c(seq, self.device)
+        T = seq.shape[0]
+        n = (T + self.frames - 1) // self.frames
+        clips = torch.empty((n, self.frames, self.num_kps, 2), dtype=torch.float32, device=self.device)
+        flip = torch.empty_like(clips) if want_flip else None
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_prepare_clips(self.handle, _ptr(seq), T, _ptr(clips), _ptr(flip), _stream()),
+                  "pafuse_prepare_clips")
+        return clips, flip
+
+    def stitch_clips(self, pred, T):
+        pred = _f32c(pred, self.device)
+        n, K, H = pred.shape[0], pred.shape[1], pred.shape[2]
+        out = torch.empty((K, H, T, self.num_kps, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_stitch_clips(self.handle, _ptr(pred), n, K, H, T, _ptr(out), _stream()),
+                  "pafuse_stitch_clips")
+        return out
+
+    def keypoints_from_detections(self, raw, width, height):
+        raw = _f32c(raw, self.device)
+        T = raw.shape[0]
+        kp = torch.empty((T, self.num_kps, 2), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_keypoints_from_detections(self.handle, _ptr(raw), T, int(width), int(height), _ptr(kp),
+                                                            _stream()), "pafuse_keypoints_from_detections")
+        return kp
 
     PROFILE_CATEGORIES = ("gemm", "attention", "layernorm", "embed_head", "ddim", "post")
 

@@ -545,4 +545,114 @@ int launch_aggregate(const AggParams& p, cudaStream_t st) {
     return 0;
 }
 
+// ------------------------------------------------------------------ caller-side preparation
+// eval_data_prepare (main_h3wb.py:122-154 / in_the_wild/utils.py:279-320) fused with the flip-TTA input
+// construction of the callers (main_h3wb.py:268-270, in_the_wild/utils.py:340-342):
+//   clips[i, f]      = seq[src(i, f)]            src = i*F + f for i < n-1; the last clip is the last F frames of the
+//                                                sequence, a sequence shorter than F is padded by repeating its last frame
+//   clips_flip[i, f, j] = (-x, y) of seq[src(i, f), flip_perm[j]]
+__global__ void prepare_clips_kernel(const float* __restrict__ seq, long long T, int F, int J,
+                                     const int* __restrict__ flip_perm, float* __restrict__ clips,
+                                     float* __restrict__ clips_flip, long long n_clips) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_clips * F * J) return;
+    const int j = (int)(idx % J);
+    long long t = idx / J;
+    const int f = (int)(t % F);
+    const long long i = t / F;
+    long long src;
+    if (i < n_clips - 1) {
+        src = i * F + f;
+    } else {
+        src = (T > F ? T - F : 0) + f;
+        if (src > T - 1) src = T - 1;
+    }
+    const float2 v = *reinterpret_cast<const float2*>(seq + ((size_t)src * J + j) * 2);
+    *reinterpret_cast<float2*>(clips + (size_t)idx * 2) = v;
+    if (clips_flip) {
+        const float2 w = *reinterpret_cast<const float2*>(seq + ((size_t)src * J + flip_perm[j]) * 2);
+        *reinterpret_cast<float2*>(clips_flip + (size_t)idx * 2) = make_float2(-w.x, w.y);
+    }
+}
+
+int launch_prepare_clips(const float* seq, long long T, int F, int J, const int* flip_perm, float* clips,
+                         float* clips_flip, long long n_clips, cudaStream_t st) {
+    const long long total = n_clips * F * J;
+    if (total == 0) return 0;
+    prepare_clips_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(seq, T, F, J, flip_perm, clips, clips_flip, n_clips);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// Clips back to the sequence (in_the_wild/h3wb_diffusion.py:119-133): pred [n,K,H,F,J,3] -> out [K,H,T,J,3]; frame t
+// comes from clip t / F while t is inside a full clip, the remaining T mod F frames are the LAST ones of the last clip.
+__global__ void stitch_clips_kernel(const float* __restrict__ pred, float* __restrict__ out, long long n_clips, int K,
+                                    int H, int F, int J, long long T) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)K * H * T * J;
+    if (idx >= total) return;
+    const int j = (int)(idx % J);
+    long long r = idx / J;
+    const long long t = r % T;
+    r /= T;
+    const int h = (int)(r % H);
+    const int k = (int)(r / H);
+    const long long full = T / F;
+    long long clip;
+    int f;
+    if (t < full * F) {
+        clip = t / F;
+        f = (int)(t % F);
+    } else {
+        clip = n_clips - 1;
+        f = F - (int)(T - t);
+    }
+    const float* src = pred + (((((size_t)clip * K + k) * H + h) * F + f) * J + j) * 3;
+    float* dst = out + (size_t)idx * 3;
+    dst[0] = src[0];
+    dst[1] = src[1];
+    dst[2] = src[2];
+}
+
+int launch_stitch_clips(const float* pred, float* out, long long n_clips, int K, int H, int F, int J, long long T,
+                        cudaStream_t st) {
+    const long long total = (long long)K * H * T * J;
+    if (total == 0) return 0;
+    stitch_clips_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pred, out, n_clips, K, H, F, J, T);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// OpenPifPaf detections -> normalised H3WB input (in_the_wild/h3wb_diffusion.py:64-77, common/camera.py:7-11):
+// raw [T, J-1, 3] (x, y, confidence in pixels) -> kp [T, J, 2]: joints 1.. are the detections, joint 0 is the mean of
+// joints 12 and 13 (fp32), then X / w * 2 - [1, h / w] with the subtraction in fp64 like numpy (float32 array minus
+// a python-float list) and one rounding to fp32 (the callers' astype('float32')).
+__global__ void keypoints_kernel(const float* __restrict__ raw, float* __restrict__ kp, long long T, int J, float w,
+                                 double hw) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T * J) return;
+    const int j = (int)(idx % J);
+    const long long t = idx / J;
+    const float* fr = raw + (size_t)t * (J - 1) * 3;
+    float x, y;
+    if (j == 0) {
+        x = __fdiv_rn(__fadd_rn(fr[11 * 3], fr[12 * 3]), 2.0f);          // joints 12, 13 = detections 11, 12
+        y = __fdiv_rn(__fadd_rn(fr[11 * 3 + 1], fr[12 * 3 + 1]), 2.0f);
+    } else {
+        x = fr[(j - 1) * 3];
+        y = fr[(j - 1) * 3 + 1];
+    }
+    const float nx = __fmul_rn(__fdiv_rn(x, w), 2.0f), ny = __fmul_rn(__fdiv_rn(y, w), 2.0f);
+    kp[(size_t)idx * 2] = (float)__dsub_rn((double)nx, 1.0);
+    kp[(size_t)idx * 2 + 1] = (float)__dsub_rn((double)ny, hw);
+}
+
+int launch_keypoints(const float* raw, float* kp, long long T, int J, int w, int h, cudaStream_t st) {
+    if (T == 0) return 0;
+    const long long total = T * J;
+    keypoints_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(raw, kp, T, J, (float)w, (double)h / (double)w);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
 }  // namespace pafuse

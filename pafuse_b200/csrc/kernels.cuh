@@ -139,6 +139,11 @@ int launch_negate_rows(float* x, const int* rows, int nrows, long long poses, in
 int launch_project(const float* X, const float* cam, float* out, long long npts, long long pts_per_cam,
                    cudaStream_t st);
 int launch_aggregate(const AggParams& p, cudaStream_t st);
+int launch_prepare_clips(const float* seq, long long T, int F, int J, const int* flip_perm, float* clips,
+                         float* clips_flip, long long n_clips, cudaStream_t st);
+int launch_stitch_clips(const float* pred, float* out, long long n_clips, int K, int H, int F, int J, long long T,
+                        cudaStream_t st);
+int launch_keypoints(const float* raw, float* kp, long long T, int J, int w, int h, cudaStream_t st);
 int launch_attention(const AttnParams& p, cudaStream_t st);          // CUDA-core version (debug reference)
 int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int F, int J, int C, int temporal,
                         cudaStream_t st);

@@ -651,6 +651,44 @@ int pafuse_aggregate(pafuse_ctx* ctx, const float* pred, const float* traj, cons
     return launch_aggregate(a, (cudaStream_t)stream);
 }
 
+int pafuse_prepare_clips(pafuse_ctx* ctx, const float* seq, int64_t T, float* clips, float* clips_flip, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (T == 0) return 0;
+    if (!seq || !clips || T < 0) {
+        set_last_error("pafuse_prepare_clips: bad argument");
+        return PAFUSE_E_ARG;
+    }
+    const int F = ctx->cfg.frames;
+    const long long n = (T + F - 1) / F;
+    ProfScope ps(ctx, CAT_POST, (clips_flip ? 24.0 : 16.0) * (double)n * F * ctx->cfg.num_kps, (cudaStream_t)stream);
+    return launch_prepare_clips(seq, T, F, ctx->cfg.num_kps, ctx->flip_perm_dev, clips, clips_flip, n, (cudaStream_t)stream);
+}
+
+int pafuse_stitch_clips(pafuse_ctx* ctx, const float* pred, int64_t n_clips, int32_t K, int32_t H, int64_t T, float* out,
+                        void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (T == 0) return 0;
+    const int F = ctx->cfg.frames;
+    if (!pred || !out || K < 1 || H < 1 || T < 0 || n_clips != (T + F - 1) / F) {
+        set_last_error("pafuse_stitch_clips: bad argument (n_clips=%lld must be ceil(T/F) for T=%lld)", (long long)n_clips,
+                       (long long)T);
+        return PAFUSE_E_ARG;
+    }
+    ProfScope ps(ctx, CAT_POST, 24.0 * (double)K * H * T * ctx->cfg.num_kps, (cudaStream_t)stream);
+    return launch_stitch_clips(pred, out, n_clips, K, H, F, ctx->cfg.num_kps, T, (cudaStream_t)stream);
+}
+
+int pafuse_keypoints_from_detections(pafuse_ctx* ctx, const float* raw, int64_t T, int32_t width, int32_t height, float* kp,
+                                     void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (T == 0) return 0;
+    if (!raw || !kp || T < 0 || width < 1 || height < 1 || ctx->cfg.num_kps < 14) {
+        set_last_error("pafuse_keypoints_from_detections: bad argument");
+        return PAFUSE_E_ARG;
+    }
+    return launch_keypoints(raw, kp, T, ctx->cfg.num_kps, width, height, (cudaStream_t)stream);
+}
+
 int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->debug_simt = enable != 0;

@@ -14,12 +14,14 @@ from .h3wb import H3WBSkeleton
 _contexts = {}
 
 
-def _post_context(device, num_kps=134, frames=27) -> _native.NativeContext:
-    """A weight-less context for the post-processing kernels on ``device``."""
+def _post_context(device, num_kps=134, frames=27, flip_perm=None) -> _native.NativeContext:
+    """A weight-less context for the pre-/post-processing kernels on ``device`` (``flip_perm``: the left/right
+    joint permutation the flip-TTA input construction uses; identity when not given)."""
     dev = torch.device(device)
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), num_kps, frames)
+    perm = tuple(flip_perm) if flip_perm is not None else tuple(range(num_kps))
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), num_kps, frames, perm)
     if key not in _contexts:
-        _contexts[key] = _native.NativeContext(frames, num_kps, 1, 8, [32], [[0]], list(range(num_kps)), 1.0, 1,
+        _contexts[key] = _native.NativeContext(frames, num_kps, 1, 8, [32], [[0]], list(perm), 1.0, 1,
                                                torch.device("cuda", key[0]))
     return _contexts[key]
 
@@ -86,4 +88,31 @@ def aggregate_hypotheses(pred, inputs_traj, cam, inputs_2d, return_select=False,
     return tuple(out)
 
 
-__all__ = ["wb_pose_from_parts", "project_to_2d", "aggregate_hypotheses", "connection_table", "H3WBSkeleton"]
+def eval_data_prepare(receptive_field, inputs_2d, kps_left=None, kps_right=None):
+    """Tile one 2D sequence into clips (``main_h3wb.py:122-154``, ``in_the_wild/utils.py:279-320``).
+
+    inputs_2d ``(1,T,J,2)`` or ``(T,J,2)`` CUDA tensor -> ``(ceil(T/rf), rf, J, 2)``: the last clip holds the last
+    ``rf`` frames, a sequence shorter than ``rf`` is padded by repeating its last frame.  With ``kps_left`` /
+    ``kps_right`` the flip-TTA twin the callers build first (``main_h3wb.py:268-270``: x negated, left/right
+    keypoints swapped) is produced by the same kernel and ``(clips, clips_flip)`` is returned.
+    """
+    if not inputs_2d.is_cuda:
+        raise _native.PafuseError("pafuse_b200.eval_data_prepare needs a CUDA tensor (no CPU fallback)")
+    seq = inputs_2d
+    if seq.dim() == 4:
+        assert seq.shape[0] == 1, "eval_data_prepare takes one sequence"
+        seq = seq[0]
+    assert seq.dim() == 3 and seq.shape[-1] == 2
+    J = seq.shape[1]
+    want_flip = kps_left is not None
+    perm = None
+    if want_flip:
+        from .h3wb import flip_permutation
+        perm = flip_permutation(kps_left, kps_right, J)
+    ctx = _post_context(seq.device, J, int(receptive_field), perm)
+    clips, flip = ctx.prepare_clips(seq, want_flip=want_flip)
+    return (clips, flip) if want_flip else clips
+
+
+__all__ = ["wb_pose_from_parts", "project_to_2d", "aggregate_hypotheses", "connection_table", "eval_data_prepare",
+           "H3WBSkeleton"]

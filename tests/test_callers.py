@@ -1,0 +1,110 @@
+"""Caller-side rows: flip-TTA input construction, eval_data_prepare tiling, detection ->
+keypoints normalisation, clip stitching, and the in-the-wild driver built from them.
+
+CPU tests pin the oracle against vectors the reference itself produced (tests/golden/make_golden_callers.py);
+GPU tests compare the kernels (through the C ABI) with the oracle bit for bit.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pafuse_oracle as orc
+from pafuse_testlib import load_golden
+
+
+def _golden():
+    g = load_golden("callers")
+    return {k: torch.from_numpy(g[k]) for k in g.files}
+
+
+# ------------------------------------------------------------------ oracle against the reference's vectors (CPU)
+def test_oracle_keypoints_match_reference():
+    g = _golden()
+    w, h = (int(v) for v in g["wh"])
+    assert torch.equal(orc.keypoints_from_openpifpaf(g["det"], w, h), g["kp"])
+
+
+@pytest.mark.parametrize("T", [5, 27, 54, 70])
+def test_oracle_prepare_matches_reference(T, skeleton):
+    g = _golden()
+    seq = g["kp"][:T]
+    assert torch.equal(orc.eval_data_prepare(27, seq), g[f"clips_T{T}"])
+    flip = orc.flip_inputs_2d(seq, skeleton.kps_left(), skeleton.kps_right())
+    assert torch.equal(orc.eval_data_prepare(27, flip), g[f"clips_flip_T{T}"])
+
+
+def test_oracle_flip_is_an_involution(skeleton):
+    x = torch.randn(3, 27, 134, 2)
+    L, R = skeleton.kps_left(), skeleton.kps_right()
+    assert torch.equal(orc.flip_inputs_2d(orc.flip_inputs_2d(x, L, R), L, R), x)
+
+
+# ------------------------------------------------------------------ kernels against the oracle (GPU)
+@pytest.mark.gpu
+def test_keypoints_kernel_bit_exact():
+    from pafuse_b200 import in_the_wild as itw
+    g = _golden()
+    w, h = (int(v) for v in g["wh"])
+    got = itw.keypoints_from_openpifpaf(g["det"], w, h)
+    assert torch.equal(got.cpu(), g["kp"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [1, 5, 26, 27, 28, 54, 70, 3000])
+def test_prepare_and_stitch_kernels_bit_exact(T, skeleton):
+    import pafuse_b200
+    from pafuse_b200 import in_the_wild as itw
+    gen = torch.Generator().manual_seed(T)
+    seq = torch.rand(T, 134, 2, generator=gen) * 2 - 1
+    L, R = skeleton.kps_left(), skeleton.kps_right()
+    clips, flip = pafuse_b200.eval_data_prepare(27, seq.cuda()[None], L, R)
+    assert torch.equal(clips.cpu(), orc.eval_data_prepare(27, seq))
+    assert torch.equal(flip.cpu(), orc.eval_data_prepare(27, orc.flip_inputs_2d(seq, L, R)))
+    only = pafuse_b200.eval_data_prepare(27, seq.cuda())
+    assert torch.equal(only, clips)
+    n = clips.shape[0]
+    pred = torch.randn(n, 2, 3, 27, 134, 3, generator=gen)
+    assert torch.equal(itw.stitch_predictions(pred.cuda(), T).cpu(), orc.stitch_clips(pred, T))
+
+
+@pytest.mark.gpu
+def test_golden_clips_from_the_reference(skeleton):
+    import pafuse_b200
+    g = _golden()
+    for T in (5, 27, 54, 70):
+        clips, flip = pafuse_b200.eval_data_prepare(27, g["kp"][:T].cuda(), skeleton.kps_left(), skeleton.kps_right())
+        assert torch.equal(clips.cpu(), g[f"clips_T{T}"]) and torch.equal(flip.cpu(), g[f"clips_flip_T{T}"])
+
+
+@pytest.mark.gpu
+def test_in_the_wild_driver_against_oracle(skeleton):
+    """BASELINE config 5 in miniature: 70 synthetic detection frames -> 3 clips -> lift -> stitch -> mean pose."""
+    import pafuse_b200
+    from pafuse_b200 import in_the_wild as itw
+    from pafuse_b200 import synthetic
+    from pafuse_b200.h3wb import H3WBSkeleton, merged_part_indices
+    g = _golden()
+    w, h = (int(v) for v in g["wh"])
+    T, H, K, depth = 70, 2, 2, 2
+    sd = synthetic.synthetic_state_dict(seed=3, depth=depth)
+    model = pafuse_b200.D3DP(synthetic.default_args(depth=depth), skeleton.joints_left, skeleton.joints_right, skeleton,
+                             is_train=False, num_proposals=H, sampling_timesteps=K)
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda().eval()
+    noises = synthetic.synthetic_noise(3, H, K, seed=9)
+    model.noise_source = lambda k, shape, device: noises[k].to(device)
+    kp = itw.keypoints_from_openpifpaf(g["det"], w, h)
+    res = itw.lift_video(model, H3WBSkeleton(), kp, receptive_field=27, bs=8)
+    assert res["prediction"].shape == (K, H, T, 134, 3) and res["mean_pose"].shape == (T, 134, 3)
+
+    L, R = skeleton.kps_left(), skeleton.kps_right()
+    seq = orc.keypoints_from_openpifpaf(g["det"], w, h)
+    x2d = orc.eval_data_prepare(27, seq)
+    x2df = orc.eval_data_prepare(27, orc.flip_inputs_2d(seq, L, R))
+    parts = merged_part_indices(skeleton.parts_joint_indices)
+    ref = orc.ddim_sample_flip(sd, parts, x2d, x2df, noises, skeleton.joints_left, skeleton.joints_right, H, K, depth=depth)
+    ref, _ = orc.wb_pose_from_parts(ref, skeleton.parts_joint_indices, skeleton.parts_connection_indices)
+    ref = orc.stitch_clips(ref, T)
+    d = (res["prediction"].cpu().double() - ref.double()).abs()
+    assert not (d > 1e-3 * ref.double().abs() + 2e-5).any(), d.max().item()
+    assert torch.allclose(res["mean_pose"].cpu(), ref[-1].mean(dim=0), rtol=1e-3, atol=2e-5)
