@@ -113,6 +113,15 @@ int pafuse_aggregate(pafuse_ctx* ctx, const float* pred, const float* traj, cons
                      const float* x2d, float* jagg, float* pagg, int32_t* select, float* reproj, int32_t B, int32_t K,
                      int32_t H, void* stream);
 
+/* GT-dependent multi-hypothesis MPJPE protocols of evaluate() (main_h3wb.py:344-349; common/loss.py:36-146), one pass:
+ * pred [B,K,H,F,J,3] whole-body, target [B,F,J,3]; the 2D error of J-Agg uses `reproj` [B,K,H,F,J,2] when given, else
+ * the projection of pred + traj with cam as in pafuse_aggregate.  sums (device, fp64) [K][3+H]: per sampling step the
+ * SUMS over (b,f,j) of the J-Best, P-Agg and J-Agg errors and, per hypothesis, of the root-centred error (P-Best = min
+ * over hypotheses after the division); divide by B*F*J. */
+int pafuse_mpjpe_metrics(pafuse_ctx* ctx, const float* pred, const float* target, const float* traj, const float* cam,
+                         int32_t cam_per_clip, const float* x2d, const float* reproj, double* sums, int32_t B, int32_t K,
+                         int32_t H, void* stream);
+
 /* ---- caller-side preparation (the code around the model call in main_h3wb.py / in_the_wild) ----
  *
  * pafuse_prepare_clips: eval_data_prepare (main_h3wb.py:122-154, in_the_wild/utils.py:279-320) fused with the flip-TTA

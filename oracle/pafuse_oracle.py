@@ -354,3 +354,36 @@ def keypoints_from_openpifpaf(detections, w: int, h: int) -> torch.Tensor:
     kp[:, 1:, 1] = det[:, :, 1]
     kp[:, :1, :] = (kp[:, 12:13, :] + kp[:, 13:14, :]) / 2.
     return torch.from_numpy(normalize_screen_coordinates(kp, w, h).astype("float32"))
+
+
+# --------------------------------------------------------------------------
+# GT-dependent multi-hypothesis metrics (common/loss.py:36-146, whole-body calls of main_h3wb.py:344-349)
+# --------------------------------------------------------------------------
+def mpjpe_j_best(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """mpjpe_diffusion_all_min(mean_pos=False), loss.py:53-66: (B,K,H,F,J,3), (B,F,J,3) -> (K,)."""
+    err = torch.norm(pred - target[:, None, None], dim=-1)            # b k h f j
+    return err.min(dim=2).values.permute(1, 0, 2, 3).reshape(pred.shape[1], -1).mean(dim=-1)
+
+
+def mpjpe_p_agg(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """mpjpe_diffusion_all_min(mean_pos=True), loss.py:68-76."""
+    err = torch.norm(pred.mean(dim=2) - target[:, None], dim=-1)      # b k f j
+    return err.permute(1, 0, 2, 3).reshape(pred.shape[1], -1).mean(dim=-1)
+
+
+def mpjpe_j_agg(pred: torch.Tensor, target: torch.Tensor, reproj_2d: torch.Tensor, target_2d: torch.Tensor) -> torch.Tensor:
+    """mpjpe_diffusion_reproj, loss.py:90-112."""
+    err = torch.norm(pred - target[:, None, None], dim=-1)
+    err2d = torch.norm(reproj_2d - target_2d[:, None, None], dim=-1)
+    sel = err2d.min(dim=2, keepdim=True).indices
+    picked = torch.gather(err, 2, sel)
+    return picked.permute(1, 2, 0, 3, 4).reshape(pred.shape[1], -1).mean(dim=-1)
+
+
+def mpjpe_p_best(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """mpjpe_diffusion(mean_pos=False, part_based=False), loss.py:114-146 (both poses root-centred first, :131-132)."""
+    p = pred - pred[..., 0:1, :]
+    t = target - target[..., 0:1, :]
+    err = torch.norm(p - t[:, None, None], dim=-1)                    # b k h f j
+    K, H = pred.shape[1], pred.shape[2]
+    return err.permute(1, 2, 0, 3, 4).reshape(K, H, -1).mean(dim=-1).min(dim=1).values

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "pafuse_project_to_2d": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "pafuse_aggregate": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "pafuse_mpjpe_metrics": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                       c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "pafuse_prepare_clips": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "pafuse_stitch_clips": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "pafuse_keypoints_from_detections": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
@@ -257,6 +259,20 @@ class NativeContext:
 
     def set_debug_simt_gemm(self, enable: bool):
         check(self.lib.pafuse_set_debug_simt_gemm(self.handle, 1 if enable else 0), "pafuse_set_debug_simt_gemm")
+
+    def mpjpe_metrics(self, pred, target, traj, cam, x2d, reproj=None):
+        pred, target, x2d = _f32c(pred, self.device), _f32c(target, self.device), _f32c(x2d, self.device)
+        traj = None if traj is None else _f32c(traj, self.device)
+        cam = None if cam is None else _f32c(cam, self.device)
+        reproj = None if reproj is None else _f32c(reproj, self.device)
+        B, K, H, F, J, _ = pred.shape
+        sums = torch.empty((K, 3 + H), dtype=torch.float64, device=self.device)
+        cam_per_clip = 1 if (cam is not None and cam.dim() == 2 and cam.shape[0] == B and B > 1) else 0
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_mpjpe_metrics(self.handle, _ptr(pred), _ptr(target), _ptr(traj), _ptr(cam), cam_per_clip,
+                                                _ptr(x2d), _ptr(reproj), _ptr(sums), B, K, H, _stream()),
+                  "pafuse_mpjpe_metrics")
+        return sums / float(B * F * J)
 
     # ---- caller-side preparation
     def prepare_clips(self, seq, want_flip=True):

@@ -655,4 +655,111 @@ int launch_keypoints(const float* raw, float* kp, long long T, int J, int w, int
     return 0;
 }
 
+// ------------------------------------------------------------------ GT-dependent multi-hypothesis metrics
+// The four whole-body MPJPE protocols evaluate() accumulates (main_h3wb.py:344-349) in one pass over the predictions:
+//   J-Best  mpjpe_diffusion_all_min(mean_pos=False)  common/loss.py:53-66   per joint min over hypotheses of |p - g|
+//   P-Agg   mpjpe_diffusion_all_min(mean_pos=True)   common/loss.py:68-76   |mean_h p - g|
+//   J-Agg   mpjpe_diffusion_reproj                   common/loss.py:90-112  |p - g| of the hypothesis with the smallest 2D
+//                                                                           reprojection error (first minimum)
+//   P-Best  mpjpe_diffusion(mean_pos=False)          common/loss.py:114-146 per hypothesis mean of the root-centred error
+//                                                                           (the host takes the min over hypotheses)
+// One thread per (b, k, f, j); a block shares (b, k) and adds its partial sums (fp64) to out[k][0..2] and out[k][3+h].
+__global__ void metrics_kernel(AggParams p, const float* __restrict__ target, const float* __restrict__ reproj_in,
+                               double* __restrict__ out) {
+    const int bk = blockIdx.y;
+    const int k = bk % p.K;
+    const long long b = bk / p.K;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;          // (f, j)
+    const int FJ = p.F * p.J;
+    const bool live = item < FJ;
+    extern __shared__ double red[];                                   // [(3 + H)][warps]
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float jbest = 0.f, jagg = 0.f, pagg = 0.f;
+    const int f = live ? item / p.J : 0, j = live ? item % p.J : 0;
+    const float* g = target + (((size_t)b * p.F + f) * p.J + j) * 3;
+    const float* g0 = target + (((size_t)b * p.F + f) * p.J) * 3;    // root joint of the frame
+    const float* tr = p.traj ? p.traj + ((size_t)b * p.F + f) * 3 : nullptr;
+    const float* tgt2 = p.x2d + (((size_t)b * p.F + f) * p.J + j) * 2;
+    const float* cam = p.cam + (p.cam_per_clip ? b * 9 : 0);
+    float gv[3] = {0.f, 0.f, 0.f}, gc[3] = {0.f, 0.f, 0.f}, sum[3] = {0.f, 0.f, 0.f};
+    if (live) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            gv[c] = g[c];
+            gc[c] = __fsub_rn(g[c], g0[c]);
+        }
+    }
+    float best2d = 0.f;
+    for (int h = 0; h < p.H; ++h) {
+        float e_c = 0.f;
+        if (live) {
+            const size_t base = ((((size_t)b * p.K + k) * p.H + h) * p.F + f) * p.J;
+            const float* x = p.pred + (base + j) * 3;
+            const float* x0 = p.pred + base * 3;
+            float d[3], dc[3], xa[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float xv = x[c];
+                d[c] = __fsub_rn(xv, gv[c]);
+                dc[c] = __fsub_rn(__fsub_rn(xv, x0[c]), gc[c]);
+                xa[c] = tr ? __fadd_rn(xv, tr[c]) : xv;
+                sum[c] = h == 0 ? xv : __fadd_rn(sum[c], xv);
+            }
+            const float e = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+            e_c = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dc[0], dc[0]), __fmul_rn(dc[1], dc[1])), __fmul_rn(dc[2], dc[2])));
+            float uv[2];
+            if (reproj_in) {
+                const float* r2 = reproj_in + (base + j) * 2;
+                uv[0] = r2[0];
+                uv[1] = r2[1];
+            } else {
+                project_point(xa, cam, uv);
+            }
+            const float d0 = __fsub_rn(uv[0], tgt2[0]), d1 = __fsub_rn(uv[1], tgt2[1]);
+            const float e2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));
+            if (h == 0 || e < jbest) jbest = e;
+            if (h == 0 || e2 < best2d) {
+                best2d = e2;
+                jagg = e;
+            }
+        }
+        // per-hypothesis sum of the root-centred error over the block
+        double v = (double)e_c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[(3 + h) * nwarp + warp] = v;
+    }
+    if (live) {
+        const float hf = (float)p.H;
+        float m[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) m[c] = __fsub_rn(__fdiv_rn(sum[c], hf), gv[c]);
+        pagg = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], m[0]), __fmul_rn(m[1], m[1])), __fmul_rn(m[2], m[2])));
+    }
+    double v3[3] = {(double)jbest, (double)pagg, (double)jagg};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double v = v3[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[q * nwarp + warp] = v;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < 3 + p.H; q += blockDim.x) {
+        double v = 0.0;
+        for (int w = 0; w < nwarp; ++w) v += red[q * nwarp + w];
+        atomicAdd(out + (size_t)k * (3 + p.H) + q, v);
+    }
+}
+
+int launch_metrics(const AggParams& p, const float* target, const float* reproj_in, double* out, cudaStream_t st) {
+    if ((long long)p.B * p.K == 0) return 0;
+    const int threads = 256;
+    dim3 grid((unsigned)((p.F * p.J + threads - 1) / threads), (unsigned)(p.B * p.K));
+    const size_t smem = (size_t)(3 + p.H) * (threads / 32) * sizeof(double);
+    metrics_kernel<<<grid, threads, smem, st>>>(p, target, reproj_in, out);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
 }  // namespace pafuse

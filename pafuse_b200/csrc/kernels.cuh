@@ -143,6 +143,7 @@ int launch_prepare_clips(const float* seq, long long T, int F, int J, const int*
                          float* clips_flip, long long n_clips, cudaStream_t st);
 int launch_stitch_clips(const float* pred, float* out, long long n_clips, int K, int H, int F, int J, long long T,
                         cudaStream_t st);
+int launch_metrics(const AggParams& p, const float* target, const float* reproj_in, double* out, cudaStream_t st);
 int launch_keypoints(const float* raw, float* kp, long long T, int J, int w, int h, cudaStream_t st);
 int launch_attention(const AttnParams& p, cudaStream_t st);          // CUDA-core version (debug reference)
 int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int F, int J, int C, int temporal,

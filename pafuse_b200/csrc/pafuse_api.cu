@@ -651,6 +651,24 @@ int pafuse_aggregate(pafuse_ctx* ctx, const float* pred, const float* traj, cons
     return launch_aggregate(a, (cudaStream_t)stream);
 }
 
+int pafuse_mpjpe_metrics(pafuse_ctx* ctx, const float* pred, const float* target, const float* traj, const float* cam,
+                         int32_t cam_per_clip, const float* x2d, const float* reproj, double* sums, int32_t B, int32_t K,
+                         int32_t H, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!pred || !target || !x2d || !sums || (!reproj && !cam) || B < 0 || K < 1 || H < 1 || H > 256 || (long long)B * K > 65535) {
+        set_last_error("pafuse_mpjpe_metrics: bad argument (B*K <= 65535, H <= 256)");
+        return PAFUSE_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    PAFUSE_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)K * (3 + H) * sizeof(double), st));
+    AggParams a;
+    a.B = B; a.K = K; a.H = H; a.F = ctx->cfg.frames; a.J = ctx->cfg.num_kps; a.cam_per_clip = cam_per_clip;
+    a.pred = pred; a.traj = traj; a.cam = cam; a.x2d = x2d; a.jagg = nullptr; a.pagg = nullptr; a.select = nullptr;
+    a.reproj = nullptr;
+    ProfScope ps(ctx, CAT_POST, 12.0 * a.F * a.J * ((double)B * K * H + B), st);
+    return launch_metrics(a, target, reproj, sums, st);
+}
+
 int pafuse_prepare_clips(pafuse_ctx* ctx, const float* seq, int64_t T, float* clips, float* clips_flip, void* stream) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     if (T == 0) return 0;

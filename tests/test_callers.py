@@ -108,3 +108,42 @@ def test_in_the_wild_driver_against_oracle(skeleton):
     d = (res["prediction"].cpu().double() - ref.double()).abs()
     assert not (d > 1e-3 * ref.double().abs() + 2e-5).any(), d.max().item()
     assert torch.allclose(res["mean_pose"].cpu(), ref[-1].mean(dim=0), rtol=1e-3, atol=2e-5)
+
+
+# ------------------------------------------------------------------ GT-dependent metrics
+def test_oracle_metrics_match_reference_loss_functions():
+    g = _golden()
+    pred, target, t2d, rep = g["m_pred"], g["m_target"], g["m_target_2d"], g["m_reproj"]
+    assert torch.allclose(orc.mpjpe_j_best(pred, target), g["m_j_best"], rtol=1e-6, atol=0)
+    assert torch.allclose(orc.mpjpe_p_agg(pred, target), g["m_p_agg"], rtol=1e-6, atol=0)
+    assert torch.allclose(orc.mpjpe_j_agg(pred, target, rep, t2d), g["m_j_agg"], rtol=1e-6, atol=0)
+    assert torch.allclose(orc.mpjpe_p_best(pred, target), g["m_p_best"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.gpu
+def test_metrics_kernel_against_reference_values():
+    from pafuse_b200 import loss
+    g = _golden()
+    pred, target, t2d, rep = (g[k].cuda() for k in ("m_pred", "m_target", "m_target_2d", "m_reproj"))
+    tol = dict(rtol=2e-6, atol=0)                                      # fp32 means of the reference vs fp64 sums here
+    assert torch.allclose(loss.mpjpe_diffusion_all_min(pred, target).cpu(), g["m_j_best"], **tol)
+    assert torch.allclose(loss.mpjpe_diffusion_all_min(pred, target, mean_pos=True).cpu(), g["m_p_agg"], **tol)
+    assert torch.allclose(loss.mpjpe_diffusion_reproj(pred, target, rep, t2d).cpu(), g["m_j_agg"], **tol)
+    assert torch.allclose(loss.mpjpe_diffusion(pred, target)[0].cpu(), g["m_p_best"], **tol)
+
+
+@pytest.mark.gpu
+def test_evaluate_metrics_is_consistent_with_aggregation():
+    """J-Agg / P-Agg errors of evaluate_metrics == errors of the poses aggregate_hypotheses returns."""
+    import pafuse_b200
+    from pafuse_b200 import loss, synthetic
+    g = _golden()
+    pred, target, t2d = (g[k].cuda() for k in ("m_pred", "m_target", "m_target_2d"))
+    B = pred.shape[0]
+    traj, cam = synthetic.synthetic_trajectory(B, seed=2).cuda(), synthetic.h36m_cam0_intrinsics().cuda()
+    m = loss.evaluate_metrics(pred, target, traj, cam, t2d)
+    jagg, pagg = pafuse_b200.aggregate_hypotheses(pred, traj, cam, t2d)
+    ej = (jagg - target[:, None]).norm(dim=-1).permute(1, 0, 2, 3).reshape(pred.shape[1], -1).double().mean(dim=-1)
+    ep = (pagg - target[:, None]).norm(dim=-1).permute(1, 0, 2, 3).reshape(pred.shape[1], -1).double().mean(dim=-1)
+    assert torch.allclose(m["J-Agg"].double(), ej, rtol=2e-6) and torch.allclose(m["P-Agg"].double(), ep, rtol=2e-6)
+    assert (m["J-Best"] <= m["J-Agg"] + 1e-7).all() and (m["J-Best"] <= m["P-Best"] + 1e-7).all()
