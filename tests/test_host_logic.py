@@ -93,3 +93,31 @@ def test_training_branch_is_refused():
     except NotImplementedError:
         return
     raise AssertionError("training forward must raise")
+
+
+def test_config_loader_reads_the_reference_yaml_layout(tmp_path):
+    from pafuse_b200 import config
+    cfg = config.load_config()
+    assert cfg.model.number_of_frames == 27 and cfg.ft2d.num_proposals == 10 and cfg.general.part_based_model is True
+    y = tmp_path / "config.yaml"
+    y.write_text("general:\n  part_based_model: True\nmodel:\n  dep: 4  # depth\n  number_of_frames: 27\nft2d:\n  sampling_timesteps: 3\n")
+    cfg = config.load_config(str(y), overrides=["ft2d.num_proposals=20", "model.test_time_augmentation=false"])
+    assert cfg.model.dep == 4 and cfg.ft2d.sampling_timesteps == 3 and cfg.ft2d.num_proposals == 20
+    assert cfg.model.test_time_augmentation is False and cfg.data.num_kps == 134      # default kept
+
+
+def test_checkpoint_file_in_the_reference_format_loads(tmp_path):
+    """save_state layout of common/logging.py:94-104 with DataParallel key prefixes."""
+    import pafuse_b200
+    from pafuse_b200 import config, synthetic
+    from pafuse_b200.h3wb import H3WBSkeleton
+    sd = synthetic.synthetic_state_dict(seed=2, depth=1)
+    path = tmp_path / "pafuse_model.bin"
+    torch.save({"epoch": 3, "lr": 1e-4, "optimizer": {}, "model_pos": {"module." + k: v for k, v in sd.items()}}, path)
+    loaded = config.load_checkpoint(str(path))
+    sk = H3WBSkeleton()
+    m = pafuse_b200.D3DP(synthetic.default_args(depth=1), sk.joints_left, sk.joints_right, sk, is_train=False)
+    missing, unexpected = m.load_state_dict(loaded, strict=False)
+    assert not unexpected and all(not k.startswith("pose_estimator") for k in missing)
+    k = "pose_estimator.face.STEblocks.0.attn.qkv.weight"
+    assert torch.equal(m.state_dict()[k], sd[k])
