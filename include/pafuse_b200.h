@@ -176,6 +176,12 @@ int pafuse_set_debug_simt_attention(pafuse_ctx* ctx, int32_t enable);
 /* 1 (default): the LayerNorms that follow the proj / fc2 GEMMs are computed in their epilogues for parts whose
  * channel width fits one output tile (C <= 256); 0: separate LayerNorm launches everywhere */
 int pafuse_set_fuse_layernorm(pafuse_ctx* ctx, int32_t enable);
+/* 1: the part denoisers (body / face / hands, independent until the DDIM update: diffusionpose.py:163-172) run
+ * side by side, each on its own stream and on a share of the SMs, so that the DRAM-bound kernels of one part
+ * overlap the tensor-bound kernels of another; 0 (default; the overlap measured neutral on power-capped B200s):
+ * one after the other on the caller's stream.  Results are bit-identical either way.
+ * shares: SMs per part (NULL = proportional to J*C). */
+int pafuse_set_part_streams(pafuse_ctx* ctx, int32_t enable, const int32_t* shares);
 /* process-wide: 2 (default) = tcgen05 CTA pairs (cta_group::2, 256-row tiles), 1 = lone CTAs */
 int pafuse_set_gemm_cta_group(int32_t cta_group);
 /* process-wide: 1 (default) = weight-stationary GEMM tiles where the W slice fits in shared memory, 0 = always stream W */

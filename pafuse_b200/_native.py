@@ -59,6 +59,7 @@ _SIGNATURES = {
     "pafuse_set_gemm_cta_group": (c_int32, [c_int32]),
     "pafuse_set_gemm_weight_stationary": (c_int32, [c_int32]),
     "pafuse_set_fuse_layernorm": (c_int32, [c_void_p, c_int32]),
+    "pafuse_set_part_streams": (c_int32, [c_void_p, c_int32, c_void_p]),
     "pafuse_set_debug_simt_attention": (c_int32, [c_void_p, c_int32]),
 }
 
@@ -326,6 +327,12 @@ class NativeContext:
 
     def set_fuse_layernorm(self, enable: bool):
         check(self.lib.pafuse_set_fuse_layernorm(self.handle, 1 if enable else 0), "pafuse_set_fuse_layernorm")
+
+    def set_part_streams(self, enable: bool, shares=None):
+        arr = None
+        if shares is not None:
+            arr = (c_int32 * len(shares))(*[int(v) for v in shares])
+        check(self.lib.pafuse_set_part_streams(self.handle, 1 if enable else 0, arr), "pafuse_set_part_streams")
 
     def set_gemm_weight_stationary(self, enable: bool):
         with torch.cuda.device(self.device):

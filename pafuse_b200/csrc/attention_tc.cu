@@ -166,6 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         n_live += (g < p.G && q * 32 - g * Lp < L) ? 1 : 0;
     }
 
+    pdl_launch_dependents();
     // rows no box ever writes must not hold NaN bit patterns (0 * NaN in the PV product)
     for (int i = threadIdx.x; i < 2 * STAGE_BYTES / 16; i += ATT_THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -195,6 +196,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    pdl_wait();                                                // the planes come from the preceding kernel
 
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");                   // control warpgroup donates registers ...
@@ -571,7 +573,7 @@ int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int h
 }
 
 template <int HDP, int LT, bool SEP>
-int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, cudaStream_t st) {
+int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, cudaStream_t st, int sms) {
     const int SMEM = 2 * 6 * TILE_ROWS * HDP * 2 + 8 * p.stg_warp_bytes + 1024;
     if (SMEM > 227 * 1024) {
         set_last_error("attention_tc: head_dim %d needs %d bytes of shared memory", p.hd, SMEM);
@@ -584,8 +586,11 @@ int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& 
         configured = SMEM;
     }
     const long long units = (long long)p.num_tiles * 8;
-    const int grid = (int)(units < g_sms ? units : g_sms);
-    kern<<<grid, ATT_THREADS, SMEM, st>>>(mh, ml, p);
+    int grid = (int)(units < sms ? units : sms);
+    // on an SM share the CTAs are placed as pairs (no cluster feature is used), so that the share keeps whole
+    // TPCs and the CTA pairs of the GEMMs running next to it on other streams still find two free SMs together
+    const int cluster = sms < g_sms && grid % 2 == 0 ? 2 : 1;
+    PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(ATT_THREADS), (size_t)SMEM, st, cluster, mh, ml, p));
     PAFUSE_LAUNCH_OK();
     return 0;
 }
@@ -593,9 +598,10 @@ int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& 
 }  // namespace
 
 int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int F, int J, int C, int temporal,
-                        cudaStream_t st) {
+                        cudaStream_t st, int sm_limit) {
     if (S == 0) return 0;
     if (int rc = att_init()) return rc;
+    const int sms = sm_limit > 0 && sm_limit < g_sms ? sm_limit : g_sms;
     const int hd = C / 8, hds = attn_head_store(hd), hdp = hds > 32 ? 64 : 32;
     const int L = temporal ? F : J;
     if (hd > 64 || hd % 4 != 0 || L > 128 || pl.hds != hds || pl.rows_cap != (long long)S * F * J) {
@@ -668,7 +674,7 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
     // the group lengths of the H3WB parts get compile-time masks; anything else runs the generic instance
 #define PAFUSE_ATT_CASE(HDPV, LV)                                                             \
     if (hdp == HDPV && (LV == 0 || L == LV))                                                  \
-        return sep ? launch_tc<HDPV, LV, true>(mh, ml, p, st) : launch_tc<HDPV, LV, false>(mh, ml, p, st);
+        return sep ? launch_tc<HDPV, LV, true>(mh, ml, p, st, sms) : launch_tc<HDPV, LV, false>(mh, ml, p, st, sms);
     PAFUSE_ATT_CASE(64, 24)
     PAFUSE_ATT_CASE(64, 27)
     PAFUSE_ATT_CASE(64, 0)

@@ -36,6 +36,44 @@ extern thread_local long long g_launch_count;  // kernels launched by this libra
         }                                                                                 \
     } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the denoiser chain is launched with programmaticStreamSerialization and runs
+//   pdl_launch_dependents();  ... set-up that touches no global data ...  pdl_wait();
+// so the next kernel's CTAs become resident, and run their prologue (barrier init, tensor-memory allocation,
+// tensor-map prefetch, shared-memory clearing), while the tail of this kernel drains.  pdl_wait() returns once
+// the preceding grid has completed and its writes are visible; without the launch attribute it is a no-op.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();                             // PAFUSE_PDL=0 turns the launch attribute off
+
+// <<<grid, block, smem, st>>> with the programmatic-serialization attribute (and an optional cluster size)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                                Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)cluster;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = (unsigned)na;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- fp16 hi/lo split
 // Tensor-core operand format of the whole path ("f16x3"): an fp32 value v is carried as
 //   hi = fp16(v), lo = fp16(v - hi)      ->  hi + lo keeps ~22 significant bits,

@@ -94,6 +94,8 @@ int launch_time_mlp(const float* sinus, const float* w1, const float* b1, const 
 // x is negated and left/right joints are swapped on the fly (:195-198).
 // One warp per token row; lanes stride over channels.
 __global__ void embed_kernel(EmbedParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     int warps_per_block = blockDim.x >> 5;
     long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (m >= p.M) return;
@@ -140,7 +142,7 @@ int launch_embed(const EmbedParams& p, cudaStream_t st) {
     if (p.M == 0) return 0;
     const int wpb = 8;
     long long blocks = (p.M + wpb - 1) / wpb;
-    embed_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(p);
+    PAFUSE_CUDA_OK(launch_chain(embed_kernel, dim3((unsigned)blocks), dim3(wpb * 32), 0, st, 1, p));
     PAFUSE_LAUNCH_OK();
     return 0;
 }
@@ -172,6 +174,8 @@ __device__ __forceinline__ void ln_row_stats(const float4 (&v)[NV], int lane, in
 
 template <int NV>
 __global__ void __launch_bounds__(256) ln_chain_kernel(LnParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warps_per_block = blockDim.x >> 5;
     const long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (m >= p.M) return;
@@ -246,9 +250,9 @@ int launch_ln_chain(const LnParams& p, cudaStream_t st) {
         return -1;
     }
     if (p.C <= 256)
-        ln_chain_kernel<2><<<blocks, wpb * 32, 0, st>>>(p);
+        PAFUSE_CUDA_OK(launch_chain(ln_chain_kernel<2>, dim3(blocks), dim3(wpb * 32), 0, st, 1, p));
     else
-        ln_chain_kernel<3><<<blocks, wpb * 32, 0, st>>>(p);
+        PAFUSE_CUDA_OK(launch_chain(ln_chain_kernel<3>, dim3(blocks), dim3(wpb * 32), 0, st, 1, p));
     PAFUSE_LAUNCH_OK();
     return 0;
 }
@@ -259,6 +263,8 @@ int launch_ln_chain(const LnParams& p, cudaStream_t st) {
 // part's joint ids (replaces torch.cat, diffusionpose.py:165-171).
 template <int MAXV>
 __global__ void head_kernel(HeadParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     int warps_per_block = blockDim.x >> 5;
     long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (m >= p.M) return;
@@ -321,9 +327,9 @@ int launch_head(const HeadParams& p, cudaStream_t st) {
     const int wpb = 8;
     unsigned blocks = (unsigned)((p.M + wpb - 1) / wpb);
     if (p.C <= 256)
-        head_kernel<8><<<blocks, wpb * 32, 0, st>>>(p);
+        PAFUSE_CUDA_OK(launch_chain(head_kernel<8>, dim3(blocks), dim3(wpb * 32), 0, st, 1, p));
     else if (p.C <= 384)
-        head_kernel<12><<<blocks, wpb * 32, 0, st>>>(p);
+        PAFUSE_CUDA_OK(launch_chain(head_kernel<12>, dim3(blocks), dim3(wpb * 32), 0, st, 1, p));
     else {
         set_last_error("head: C=%d > 384 unsupported", p.C);
         return -1;

@@ -390,6 +390,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     const int num_kb = (p.K + a_bk - 1) / a_bk;
     const TileWalk<WRES> walk(p, (int)blockIdx.x / CG, (int)gridDim.x / CG);
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tm_a_hi);
         prefetch_tensormap(&tm_a_lo);
@@ -419,11 +420,14 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     if (CG == 2) cluster_sync_all(); else __syncthreads();    // peers' barriers are initialised past this point
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    // everything above ran while the preceding kernel was still draining; the weight-stationary producer also
+    // fetches its W slice (weights are not written by any kernel of the chain) before it joins the wait
+    if (!(WRES && warp == 0)) pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA loads its own operands) =====================
-        if (lane == 0 && walk.count > 0) {
-            if (WRES) {
+        if (WRES) {
+            if (lane == 0 && walk.count > 0) {
                 // the whole K extent of this group's W slice, once
                 const int n0 = walk.n_fixed * BN + (int)cta_rank * WN;
                 const int nkw = (p.K + BKW - 1) / BKW;
@@ -440,6 +444,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     }
                 }
             }
+            pdl_wait();
+        }
+        if (lane == 0 && walk.count > 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < walk.count; ++i) {
@@ -736,19 +743,8 @@ int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
                                             SMEM_LIMIT - (int)fa.sharedSizeBytes));
         configured = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = (size_t)smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PAFUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ah, al, wh, wl, o0, o1, o2, kp));
+    PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(NUM_THREADS), (size_t)smem, st, CG, ah, al, wh, wl, o0, o1,
+                                o2, kp));
     PAFUSE_LAUNCH_OK();
     return 0;
 }
@@ -787,7 +783,8 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
             return -1;
         }
     }
-    const int max_groups = g_num_sms / CG;
+    const int sms = g.sm_limit > 0 && g.sm_limit < g_num_sms ? g.sm_limit : g_num_sms;
+    const int max_groups = sms / CG > 0 ? sms / CG : 1;
     const int WN = BN / CG;
     const int slack = g.epilogue == EPI_RESID_LN ? SMEM_SLACK_LN : SMEM_SLACK;
 

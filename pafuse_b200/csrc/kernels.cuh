@@ -124,6 +124,7 @@ struct GemmArgs {
     // EPI_PLANES: N = 24*hds output columns in plane order (column n -> plane n / hds, d = n % hds)
     AttnPlanes planes = {nullptr, nullptr, 0, 0};
     GemmLnFuse ln;                      // EPI_RESID_LN
+    int sm_limit = 0;                   // > 0: use at most this many SMs (the parts run side by side on SM shares)
 };
 
 int launch_split_weights(const float* w, op_t* hi, op_t* lo, size_t n, cudaStream_t st);
@@ -147,7 +148,7 @@ int launch_metrics(const AggParams& p, const float* target, const float* reproj_
 int launch_keypoints(const float* raw, float* kp, long long T, int J, int w, int h, cudaStream_t st);
 int launch_attention(const AttnParams& p, cudaStream_t st);          // CUDA-core version (debug reference)
 int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int F, int J, int C, int temporal,
-                        cudaStream_t st);
+                        cudaStream_t st, int sm_limit = 0);
 int launch_qkv_to_planes(const float* qkv, const AttnPlanes& pl, long long M, int C, cudaStream_t st);
 // qkv weight [3C,C] / bias [3C] -> plane order with every head padded to hds rows (zero rows / zero bias)
 int launch_pack_qkv(const float* w, const float* b, float* wp, float* bp, int C, int hd, int hds, cudaStream_t st);

@@ -18,6 +18,18 @@ namespace pafuse {
 static thread_local char g_err[1024] = "";
 thread_local long long g_launch_count = 0;
 
+// Programmatic dependent launch is opt-in (PAFUSE_PDL=1): measured neutral on the power-capped B200s of this pool
+// (profiles/r1n_*), and it is suspended while the parts run side by side on SM shares, where early-resident CTAs
+// of a dependent kernel would squat on SMs of another part's share.
+thread_local int g_pdl_suspend = 0;
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("PAFUSE_PDL");
+        return e && atoi(e) != 0;
+    }();
+    return on && g_pdl_suspend == 0;
+}
+
 void set_last_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -97,7 +109,16 @@ struct pafuse_ctx {
     int* flip_perm_dev = nullptr;
     int* conn_dev = nullptr;         // scratch for wb_pose_from_parts tables
     int* conn_rows_dev = nullptr;
-    Workspace ws;
+    Workspace ws[PAFUSE_MAX_PARTS];  // [0] serves every part in the sequential mode; one per part when they run side by side
+    // side-by-side mode: the part denoisers are independent until the DDIM update, so each runs on its own stream
+    // on a share of the SMs (persistent kernels sized to the share); the HBM-bound kernels of one part (proj, fc2,
+    // attention) then overlap the tensor-bound ones of another (qkv, fc1) instead of taking turns on the whole GPU
+    bool part_streams = false;       // opt-in (PAFUSE_PART_STREAMS=1 / pafuse_set_part_streams): measured neutral on the
+                                     // power-capped B200s of this pool (1625-1647 vs 1638 frames/s, profiles/r1n_*)
+    int sm_share[PAFUSE_MAX_PARTS] = {0};
+    bool shares_fixed = false;       // set through pafuse_set_part_streams
+    cudaStream_t side[PAFUSE_MAX_PARTS] = {nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[PAFUSE_MAX_PARTS] = {nullptr};
     float* pred = nullptr;           // [S,F,num_kps,3]
     size_t pred_cap = 0;             // floats
     bool committed = false;
@@ -190,8 +211,7 @@ int dev_alloc(T** p, size_t n) {
     return 0;
 }
 
-int ensure_workspace(pafuse_ctx* ctx, long long rows_x_c) {
-    Workspace& w = ctx->ws;
+int ensure_workspace(pafuse_ctx* ctx, Workspace& w, long long rows_x_c) {
     if (rows_x_c <= w.rows_x_c) return 0;
     cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv); cudaFree(w.pl_hi); cudaFree(w.pl_lo);
     cudaFree(w.o_hi); cudaFree(w.o_lo); cudaFree(w.h_hi); cudaFree(w.h_lo);
@@ -224,6 +244,195 @@ int run_gemm(pafuse_ctx* ctx, const GemmArgs& g, cudaStream_t st) {
     return ctx->debug_simt ? launch_gemm_simt(g, st) : launch_gemm_tcgen05(g, st);
 }
 
+// One part denoiser (embed -> 2*depth blocks -> head) over the Sc sequences starting at s0, on stream st with
+// workspace w; sm_limit > 0 sizes the persistent kernels for a share of the SMs.
+int run_part(pafuse_ctx* ctx, int pi, Workspace& w, const float* x2d, const float* x2d_flip, const float* x3d,
+             int apply_clamp, int R, int H, int s0, int Sc, float* pred, cudaStream_t st, int sm_limit) {
+    const pafuse_config& cfg = ctx->cfg;
+    const int F = cfg.frames;
+    Part& p = ctx->parts[pi];
+    const int C = p.C, J = p.J;
+    const long long M = (long long)Sc * F * J;
+
+    EmbedParams e;
+    e.M = M; e.C = C; e.J = J; e.F = F; e.H = H; e.R = R; e.s0 = s0; e.num_kps = cfg.num_kps;
+    e.apply_clamp = apply_clamp;
+    e.clamp = (float)(1.1 * (double)cfg.scale);
+    e.scale = cfg.scale;
+    e.x2d = x2d; e.x2d_flip = x2d_flip; e.x3d = x3d;
+    e.part_joints = p.joints_dev; e.flip_perm = ctx->flip_perm_dev;
+    e.we = p.w("Spatial_patch_to_embedding.weight"); e.be = p.w("Spatial_patch_to_embedding.bias");
+    e.spos = p.w("Spatial_pos_embed"); e.temb = p.temb; e.x = w.x;
+    {
+        ProfScope ps(ctx, CAT_EMBED_HEAD, 4.0 * (double)M * C, st);
+        if (int rc = launch_embed(e, st)) return rc;
+    }
+
+    // Parts whose rows fit one GEMM tile (C <= 256: face, hands) run proj and fc2 with the LayerNorms that
+    // follow them fused into the epilogue (EPI_RESID_LN); the others keep the separate ln_chain launches.
+    const bool fuse = ctx->fuse_ln && !ctx->debug_simt && gemm_can_fuse_ln(C);
+    const int nblk = 2 * cfg.depth;
+    for (int blk = 0; blk < nblk; ++blk) {
+        const bool temporal = blk & 1;
+        const std::string b = std::string(temporal ? "TTEblocks." : "STEblocks.") + std::to_string(blk / 2) + ".";
+        LnParams l;
+        l.M = M; l.C = C; l.J = J; l.F = F; l.x = w.x;
+        l.g0 = l.b0 = nullptr; l.add_f = nullptr; l.eps0 = 1e-6f; l.eps1 = 1e-6f;
+        l.out_hi = w.a_hi; l.out_lo = w.a_lo;
+        if (!fuse || blk == 0) {
+            // shared norm of the previous block (+ Temporal_pos_embed before TTE 0), then norm1 -> hi/lo
+            if (blk > 0) {
+                const char* sn = temporal ? "Spatial_norm" : "Temporal_norm";   // norm that closed the previous block
+                l.g0 = p.w(std::string(sn) + ".weight");
+                l.b0 = p.w(std::string(sn) + ".bias");
+                if (blk == 1) l.add_f = p.w("Temporal_pos_embed");
+            }
+            l.g1 = p.w(b + "norm1.weight"); l.b1 = p.w(b + "norm1.bias");
+            ProfScope ps(ctx, CAT_LN, (blk > 0 ? 12.0 : 8.0) * (double)M * C, st);
+            if (int rc = launch_ln_chain(l, st)) return rc;
+        }
+
+        GemmArgs g;
+        g.a_hi = w.a_hi; g.a_lo = w.a_lo;
+        g.M = M; g.K = C; g.sm_limit = sm_limit;
+        const double L = temporal ? (double)F : (double)J;
+        if (ctx->debug_simt_attn) {
+            // debug: fp32 qkv + CUDA-core attention
+            if (!w.qkv) {
+                set_last_error("debug attention must be selected before the first pass (workspace has no fp32 qkv)");
+                return PAFUSE_E_STATE;
+            }
+            g.w_hi = p.wh(b + "attn.qkv.weight"); g.w_lo = p.wl(b + "attn.qkv.weight");
+            g.bias = p.w(b + "attn.qkv.bias");
+            g.out_f32 = w.qkv; g.out_hi = g.out_lo = nullptr;
+            g.N = 3 * C; g.epilogue = EPI_F32;
+            if (int rc = run_gemm(ctx, g, st)) return rc;
+            AttnParams a;
+            a.qkv = w.qkv; a.out_hi = w.o_hi; a.out_lo = w.o_lo;
+            a.S = Sc; a.F = F; a.J = J; a.C = C; a.temporal = temporal ? 1 : 0; a.scale = 0.f;
+            ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st);
+            if (int rc = launch_attention(a, st)) return rc;
+        } else {
+            // the qkv GEMM writes the fp16 hi/lo head planes the attention kernel loads
+            AttnPlanes pl;
+            pl.hi = w.pl_hi; pl.lo = w.pl_lo; pl.rows_cap = M; pl.hds = attn_head_store(C / 8);
+            if ((size_t)24 * M * pl.hds > w.plane_halves) {
+                set_last_error("attention plane workspace too small");
+                return PAFUSE_E_STATE;
+            }
+            g.w_hi = p.wh(b + "attn.qkv.weight_planes"); g.w_lo = p.wl(b + "attn.qkv.weight_planes");
+            g.bias = p.w(b + "attn.qkv.bias_planes");
+            g.out_f32 = nullptr; g.out_hi = g.out_lo = nullptr;
+            g.N = 24 * pl.hds; g.epilogue = EPI_PLANES; g.planes = pl;
+            {
+                ProfScope ps(ctx, CAT_GEMM, 2.0 * (double)M * 3 * C * C, st);   // algorithmic N = 3C (pad columns not counted)
+                if (int rc = ctx->debug_simt ? launch_gemm_simt(g, st) : launch_gemm_tcgen05(g, st)) return rc;
+            }
+            ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st);
+            if (int rc = launch_attention_tc(pl, w.o_hi, w.o_lo, Sc, F, J, C, temporal ? 1 : 0, st, sm_limit)) return rc;
+        }
+
+        // proj: x += o W^T + b, then norm2 -> hi/lo
+        g = GemmArgs();
+        g.M = M;
+        g.a_hi = w.o_hi; g.a_lo = w.o_lo;
+        g.w_hi = p.wh(b + "attn.proj.weight"); g.w_lo = p.wl(b + "attn.proj.weight");
+        g.bias = p.w(b + "attn.proj.bias");
+        g.out_f32 = w.x; g.N = C; g.K = C; g.epilogue = EPI_RESID;
+        if (fuse) {
+            g.epilogue = EPI_RESID_LN;
+            g.out_hi = w.a_hi; g.out_lo = w.a_lo;
+            g.ln.x = w.x;
+            g.ln.g1 = p.w(b + "norm2.weight"); g.ln.b1 = p.w(b + "norm2.bias"); g.ln.eps1 = 1e-6f;
+            g.ln.J = J; g.ln.F = F;
+        }
+        if (int rc = run_gemm(ctx, g, st)) return rc;
+        if (!fuse) {
+            l.g0 = l.b0 = nullptr; l.add_f = nullptr;
+            l.g1 = p.w(b + "norm2.weight"); l.b1 = p.w(b + "norm2.bias");
+            ProfScope ps(ctx, CAT_LN, 8.0 * (double)M * C, st);
+            if (int rc = launch_ln_chain(l, st)) return rc;
+        }
+
+        g = GemmArgs();
+        g.M = M;
+        g.a_hi = w.a_hi; g.a_lo = w.a_lo;
+        g.w_hi = p.wh(b + "mlp.fc1.weight"); g.w_lo = p.wl(b + "mlp.fc1.weight");
+        g.bias = p.w(b + "mlp.fc1.bias");
+        g.out_f32 = nullptr; g.out_hi = w.h_hi; g.out_lo = w.h_lo;
+        g.N = 2 * C; g.K = C; g.epilogue = EPI_GELU_SPLIT;
+        if (int rc = run_gemm(ctx, g, st)) return rc;
+
+        // fc2: x += h W^T + b; fused: the norm that closes this block (+ Temporal_pos_embed after STE 0) and
+        // norm1 of the next block
+        g = GemmArgs();
+        g.M = M;
+        g.a_hi = w.h_hi; g.a_lo = w.h_lo;
+        g.w_hi = p.wh(b + "mlp.fc2.weight"); g.w_lo = p.wl(b + "mlp.fc2.weight");
+        g.bias = p.w(b + "mlp.fc2.bias");
+        g.out_f32 = w.x; g.out_hi = g.out_lo = nullptr;
+        g.N = C; g.K = 2 * C; g.epilogue = EPI_RESID;
+        if (fuse && blk + 1 < nblk) {
+            const bool tnext = (blk + 1) & 1;
+            const std::string bn = std::string(tnext ? "TTEblocks." : "STEblocks.") + std::to_string((blk + 1) / 2) + ".";
+            const char* sn = temporal ? "Temporal_norm" : "Spatial_norm";       // norm that closes this block
+            g.epilogue = EPI_RESID_LN;
+            g.out_hi = w.a_hi; g.out_lo = w.a_lo;
+            g.ln.x = w.x;
+            g.ln.g0 = p.w(std::string(sn) + ".weight"); g.ln.b0 = p.w(std::string(sn) + ".bias"); g.ln.eps0 = 1e-6f;
+            if (blk == 0) g.ln.add_f = p.w("Temporal_pos_embed");
+            g.ln.g1 = p.w(bn + "norm1.weight"); g.ln.b1 = p.w(bn + "norm1.bias"); g.ln.eps1 = 1e-6f;
+            g.ln.J = J; g.ln.F = F;
+        }
+        if (int rc = run_gemm(ctx, g, st)) return rc;
+    }
+
+    HeadParams h;
+    h.M = M; h.C = C; h.J = J; h.F = F; h.s0 = s0; h.num_kps = cfg.num_kps; h.x = w.x;
+    h.g0 = p.w("Temporal_norm.weight"); h.b0 = p.w("Temporal_norm.bias"); h.eps0 = 1e-6f;
+    h.g1 = p.w("head.0.weight"); h.b1 = p.w("head.0.bias"); h.eps1 = 1e-5f;
+    h.wh = p.w("head.1.weight"); h.bh = p.w("head.1.bias");
+    h.part_joints = p.joints_dev; h.pred = pred;
+    {
+        ProfScope ps(ctx, CAT_EMBED_HEAD, 4.0 * (double)M * C, st);
+        if (int rc = launch_head(h, st)) return rc;
+    }
+    return 0;
+}
+
+// SM shares of the side-by-side mode: proportional to J*C (the parts' DRAM bytes per sequence, which is what their
+// time follows: body 26 %, face 43 %, hands 31 % of a pass), in whole CTA pairs.  PAFUSE_SM_SHARES="a,b,c" overrides.
+void pick_sm_shares(pafuse_ctx* ctx, int num_sms) {
+    const int n = ctx->num_parts;
+    if (const char* e = getenv("PAFUSE_SM_SHARES")) {
+        int v[PAFUSE_MAX_PARTS] = {0}, k = 0;
+        const char* q = e;
+        while (*q && k < n) {
+            v[k++] = atoi(q);
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (k == n) {
+            for (int i = 0; i < n; ++i) ctx->sm_share[i] = v[i] < 2 ? 2 : v[i] / 2 * 2;
+            return;
+        }
+    }
+    double tot = 0;
+    for (int i = 0; i < n; ++i) tot += (double)ctx->parts[i].J * ctx->parts[i].C;
+    int used = 0;
+    for (int i = 0; i < n; ++i) {
+        int v = (int)((double)ctx->parts[i].J * ctx->parts[i].C / tot * num_sms + 0.5) / 2 * 2;
+        if (v < 2) v = 2;
+        ctx->sm_share[i] = v;
+        used += v;
+    }
+    // the rounding remainder goes to (or comes from) the largest share
+    int big = 0;
+    for (int i = 1; i < n; ++i)
+        if (ctx->sm_share[i] > ctx->sm_share[big]) big = i;
+    ctx->sm_share[big] += (num_sms - used) / 2 * 2;
+}
+
 // One pass of the three part denoisers over S_total sequences (R originals followed,
 // when S_total == 2R, by their flip-TTA twins), chunked by cfg.max_seqs.
 int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, const float* x3d, int apply_clamp, int R,
@@ -248,167 +457,57 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
     }
     int max_seqs = cfg.max_seqs > 0 ? cfg.max_seqs : 256;
     int chunk = S_total < max_seqs ? S_total : max_seqs;
-    long long need = 0;
-    for (int pi = 0; pi < ctx->num_parts; ++pi) {
-        long long v = (long long)chunk * F * ctx->parts[pi].J * ctx->parts[pi].C;
-        if (v > need) need = v;
-    }
-    if (int rc = ensure_workspace(ctx, need)) return rc;
-    Workspace& w = ctx->ws;
-
-    for (int s0 = 0; s0 < S_total; s0 += chunk) {
-        const int Sc = (S_total - s0) < chunk ? (S_total - s0) : chunk;
+    // side by side needs the production kernels (the persistent ones can be sized to a share) and no per-launch
+    // timing (bench.py's profiled pass measures every kernel alone on the whole GPU)
+    const bool side_by_side = ctx->part_streams && ctx->num_parts > 1 && !ctx->prof.on && !ctx->debug_simt &&
+                              !ctx->debug_simt_attn;
+    if (!side_by_side) {
+        long long need = 0;
         for (int pi = 0; pi < ctx->num_parts; ++pi) {
-            Part& p = ctx->parts[pi];
-            const int C = p.C, J = p.J;
-            const long long M = (long long)Sc * F * J;
+            long long v = (long long)chunk * F * ctx->parts[pi].J * ctx->parts[pi].C;
+            if (v > need) need = v;
+        }
+        if (int rc = ensure_workspace(ctx, ctx->ws[0], need)) return rc;
+        for (int s0 = 0; s0 < S_total; s0 += chunk) {
+            const int Sc = (S_total - s0) < chunk ? (S_total - s0) : chunk;
+            for (int pi = 0; pi < ctx->num_parts; ++pi)
+                if (int rc = run_part(ctx, pi, ctx->ws[0], x2d, x2d_flip, x3d, apply_clamp, R, H, s0, Sc, pred, st, 0))
+                    return rc;
+        }
+        return 0;
+    }
 
-            EmbedParams e;
-            e.M = M; e.C = C; e.J = J; e.F = F; e.H = H; e.R = R; e.s0 = s0; e.num_kps = cfg.num_kps;
-            e.apply_clamp = apply_clamp;
-            e.clamp = (float)(1.1 * (double)cfg.scale);
-            e.scale = cfg.scale;
-            e.x2d = x2d; e.x2d_flip = x2d_flip; e.x3d = x3d;
-            e.part_joints = p.joints_dev; e.flip_perm = ctx->flip_perm_dev;
-            e.we = p.w("Spatial_patch_to_embedding.weight"); e.be = p.w("Spatial_patch_to_embedding.bias");
-            e.spos = p.w("Spatial_pos_embed"); e.temb = p.temb; e.x = w.x;
-            {
-                ProfScope ps(ctx, CAT_EMBED_HEAD, 4.0 * (double)M * C, st);
-                if (int rc = launch_embed(e, st)) return rc;
-            }
-
-            // Parts whose rows fit one GEMM tile (C <= 256: face, hands) run proj and fc2 with the LayerNorms that
-            // follow them fused into the epilogue (EPI_RESID_LN); the others keep the separate ln_chain launches.
-            const bool fuse = ctx->fuse_ln && !ctx->debug_simt && gemm_can_fuse_ln(C);
-            const int nblk = 2 * cfg.depth;
-            for (int blk = 0; blk < nblk; ++blk) {
-                const bool temporal = blk & 1;
-                const std::string b = std::string(temporal ? "TTEblocks." : "STEblocks.") + std::to_string(blk / 2) + ".";
-                LnParams l;
-                l.M = M; l.C = C; l.J = J; l.F = F; l.x = w.x;
-                l.g0 = l.b0 = nullptr; l.add_f = nullptr; l.eps0 = 1e-6f; l.eps1 = 1e-6f;
-                l.out_hi = w.a_hi; l.out_lo = w.a_lo;
-                if (!fuse || blk == 0) {
-                    // shared norm of the previous block (+ Temporal_pos_embed before TTE 0), then norm1 -> hi/lo
-                    if (blk > 0) {
-                        const char* sn = temporal ? "Spatial_norm" : "Temporal_norm";   // norm that closed the previous block
-                        l.g0 = p.w(std::string(sn) + ".weight");
-                        l.b0 = p.w(std::string(sn) + ".bias");
-                        if (blk == 1) l.add_f = p.w("Temporal_pos_embed");
-                    }
-                    l.g1 = p.w(b + "norm1.weight"); l.b1 = p.w(b + "norm1.bias");
-                    ProfScope ps(ctx, CAT_LN, (blk > 0 ? 12.0 : 8.0) * (double)M * C, st);
-                    if (int rc = launch_ln_chain(l, st)) return rc;
-                }
-
-                GemmArgs g;
-                g.a_hi = w.a_hi; g.a_lo = w.a_lo;
-                g.M = M; g.K = C;
-                const double L = temporal ? (double)F : (double)J;
-                if (ctx->debug_simt_attn) {
-                    // debug: fp32 qkv + CUDA-core attention
-                    if (!w.qkv) {
-                        set_last_error("debug attention must be selected before the first pass (workspace has no fp32 qkv)");
-                        return PAFUSE_E_STATE;
-                    }
-                    g.w_hi = p.wh(b + "attn.qkv.weight"); g.w_lo = p.wl(b + "attn.qkv.weight");
-                    g.bias = p.w(b + "attn.qkv.bias");
-                    g.out_f32 = w.qkv; g.out_hi = g.out_lo = nullptr;
-                    g.N = 3 * C; g.epilogue = EPI_F32;
-                    if (int rc = run_gemm(ctx, g, st)) return rc;
-                    AttnParams a;
-                    a.qkv = w.qkv; a.out_hi = w.o_hi; a.out_lo = w.o_lo;
-                    a.S = Sc; a.F = F; a.J = J; a.C = C; a.temporal = temporal ? 1 : 0; a.scale = 0.f;
-                    ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st);
-                    if (int rc = launch_attention(a, st)) return rc;
-                } else {
-                    // the qkv GEMM writes the fp16 hi/lo head planes the attention kernel loads
-                    AttnPlanes pl;
-                    pl.hi = w.pl_hi; pl.lo = w.pl_lo; pl.rows_cap = M; pl.hds = attn_head_store(C / 8);
-                    if ((size_t)24 * M * pl.hds > w.plane_halves) {
-                        set_last_error("attention plane workspace too small");
-                        return PAFUSE_E_STATE;
-                    }
-                    g.w_hi = p.wh(b + "attn.qkv.weight_planes"); g.w_lo = p.wl(b + "attn.qkv.weight_planes");
-                    g.bias = p.w(b + "attn.qkv.bias_planes");
-                    g.out_f32 = nullptr; g.out_hi = g.out_lo = nullptr;
-                    g.N = 24 * pl.hds; g.epilogue = EPI_PLANES; g.planes = pl;
-                    {
-                        ProfScope ps(ctx, CAT_GEMM, 2.0 * (double)M * 3 * C * C, st);   // algorithmic N = 3C (pad columns not counted)
-                        if (int rc = ctx->debug_simt ? launch_gemm_simt(g, st) : launch_gemm_tcgen05(g, st)) return rc;
-                    }
-                    ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st);
-                    if (int rc = launch_attention_tc(pl, w.o_hi, w.o_lo, Sc, F, J, C, temporal ? 1 : 0, st)) return rc;
-                }
-
-                // proj: x += o W^T + b, then norm2 -> hi/lo
-                g = GemmArgs();
-                g.M = M;
-                g.a_hi = w.o_hi; g.a_lo = w.o_lo;
-                g.w_hi = p.wh(b + "attn.proj.weight"); g.w_lo = p.wl(b + "attn.proj.weight");
-                g.bias = p.w(b + "attn.proj.bias");
-                g.out_f32 = w.x; g.N = C; g.K = C; g.epilogue = EPI_RESID;
-                if (fuse) {
-                    g.epilogue = EPI_RESID_LN;
-                    g.out_hi = w.a_hi; g.out_lo = w.a_lo;
-                    g.ln.x = w.x;
-                    g.ln.g1 = p.w(b + "norm2.weight"); g.ln.b1 = p.w(b + "norm2.bias"); g.ln.eps1 = 1e-6f;
-                    g.ln.J = J; g.ln.F = F;
-                }
-                if (int rc = run_gemm(ctx, g, st)) return rc;
-                if (!fuse) {
-                    l.g0 = l.b0 = nullptr; l.add_f = nullptr;
-                    l.g1 = p.w(b + "norm2.weight"); l.b1 = p.w(b + "norm2.bias");
-                    ProfScope ps(ctx, CAT_LN, 8.0 * (double)M * C, st);
-                    if (int rc = launch_ln_chain(l, st)) return rc;
-                }
-
-                g = GemmArgs();
-                g.M = M;
-                g.a_hi = w.a_hi; g.a_lo = w.a_lo;
-                g.w_hi = p.wh(b + "mlp.fc1.weight"); g.w_lo = p.wl(b + "mlp.fc1.weight");
-                g.bias = p.w(b + "mlp.fc1.bias");
-                g.out_f32 = nullptr; g.out_hi = w.h_hi; g.out_lo = w.h_lo;
-                g.N = 2 * C; g.K = C; g.epilogue = EPI_GELU_SPLIT;
-                if (int rc = run_gemm(ctx, g, st)) return rc;
-
-                // fc2: x += h W^T + b; fused: the norm that closes this block (+ Temporal_pos_embed after STE 0) and
-                // norm1 of the next block
-                g = GemmArgs();
-                g.M = M;
-                g.a_hi = w.h_hi; g.a_lo = w.h_lo;
-                g.w_hi = p.wh(b + "mlp.fc2.weight"); g.w_lo = p.wl(b + "mlp.fc2.weight");
-                g.bias = p.w(b + "mlp.fc2.bias");
-                g.out_f32 = w.x; g.out_hi = g.out_lo = nullptr;
-                g.N = C; g.K = 2 * C; g.epilogue = EPI_RESID;
-                if (fuse && blk + 1 < nblk) {
-                    const bool tnext = (blk + 1) & 1;
-                    const std::string bn = std::string(tnext ? "TTEblocks." : "STEblocks.") + std::to_string((blk + 1) / 2) + ".";
-                    const char* sn = temporal ? "Temporal_norm" : "Spatial_norm";       // norm that closes this block
-                    g.epilogue = EPI_RESID_LN;
-                    g.out_hi = w.a_hi; g.out_lo = w.a_lo;
-                    g.ln.x = w.x;
-                    g.ln.g0 = p.w(std::string(sn) + ".weight"); g.ln.b0 = p.w(std::string(sn) + ".bias"); g.ln.eps0 = 1e-6f;
-                    if (blk == 0) g.ln.add_f = p.w("Temporal_pos_embed");
-                    g.ln.g1 = p.w(bn + "norm1.weight"); g.ln.b1 = p.w(bn + "norm1.bias"); g.ln.eps1 = 1e-6f;
-                    g.ln.J = J; g.ln.F = F;
-                }
-                if (int rc = run_gemm(ctx, g, st)) return rc;
-            }
-
-            HeadParams h;
-            h.M = M; h.C = C; h.J = J; h.F = F; h.s0 = s0; h.num_kps = cfg.num_kps; h.x = w.x;
-            h.g0 = p.w("Temporal_norm.weight"); h.b0 = p.w("Temporal_norm.bias"); h.eps0 = 1e-6f;
-            h.g1 = p.w("head.0.weight"); h.b1 = p.w("head.0.bias"); h.eps1 = 1e-5f;
-            h.wh = p.w("head.1.weight"); h.bh = p.w("head.1.bias");
-            h.part_joints = p.joints_dev; h.pred = pred;
-            {
-                ProfScope ps(ctx, CAT_EMBED_HEAD, 4.0 * (double)M * C, st);
-                if (int rc = launch_head(h, st)) return rc;
-            }
+    if (!ctx->ev_fork) {
+        int num_sms = 0;
+        PAFUSE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        if (!ctx->shares_fixed) pick_sm_shares(ctx, num_sms);
+        PAFUSE_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        for (int pi = 1; pi < ctx->num_parts; ++pi) {
+            PAFUSE_CUDA_OK(cudaStreamCreateWithFlags(&ctx->side[pi], cudaStreamNonBlocking));
+            PAFUSE_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_join[pi], cudaEventDisableTiming));
         }
     }
-    return 0;
+    for (int pi = 0; pi < ctx->num_parts; ++pi)
+        if (int rc = ensure_workspace(ctx, ctx->ws[pi], (long long)chunk * F * ctx->parts[pi].J * ctx->parts[pi].C))
+            return rc;
+    // fork: part 0 stays on the caller's stream, the others run on side streams that start after everything the
+    // caller enqueued so far (inputs, time embeddings, the previous DDIM update) and are joined before returning
+    PAFUSE_CUDA_OK(cudaEventRecord(ctx->ev_fork, st));
+    for (int pi = 1; pi < ctx->num_parts; ++pi) PAFUSE_CUDA_OK(cudaStreamWaitEvent(ctx->side[pi], ctx->ev_fork, 0));
+    ++g_pdl_suspend;
+    int rc = 0;
+    for (int s0 = 0; s0 < S_total && !rc; s0 += chunk) {
+        const int Sc = (S_total - s0) < chunk ? (S_total - s0) : chunk;
+        for (int pi = 0; pi < ctx->num_parts && !rc; ++pi)
+            rc = run_part(ctx, pi, ctx->ws[pi], x2d, x2d_flip, x3d, apply_clamp, R, H, s0, Sc, pred,
+                          pi == 0 ? st : ctx->side[pi], ctx->sm_share[pi]);
+    }
+    --g_pdl_suspend;
+    for (int pi = 1; pi < ctx->num_parts; ++pi) {                      // join even after an error: no dangling work
+        cudaEventRecord(ctx->ev_join[pi], ctx->side[pi]);
+        cudaStreamWaitEvent(st, ctx->ev_join[pi], 0);
+    }
+    return rc;
 }
 
 bool check_ctx(pafuse_ctx* ctx) {
@@ -477,6 +576,7 @@ int pafuse_create(const pafuse_config* cfg, pafuse_ctx** out) {
     ctx->cfg.flip_perm = nullptr;
     if (int rc = gemm_init()) return rc;
     if (const char* e = getenv("PAFUSE_FUSE_LN")) ctx->fuse_ln = atoi(e) != 0;
+    if (const char* e = getenv("PAFUSE_PART_STREAMS")) ctx->part_streams = atoi(e) != 0;
     *out = ctx;
     return 0;
 }
@@ -487,9 +587,15 @@ void pafuse_destroy(pafuse_ctx* ctx) {
         Part& p = ctx->parts[pi];
         cudaFree(p.f32); cudaFree(p.hi); cudaFree(p.lo); cudaFree(p.joints_dev); cudaFree(p.temb);
     }
-    Workspace& w = ctx->ws;
-    cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv); cudaFree(w.pl_hi); cudaFree(w.pl_lo);
-    cudaFree(w.o_hi); cudaFree(w.o_lo); cudaFree(w.h_hi); cudaFree(w.h_lo);
+    for (Workspace& w : ctx->ws) {
+        cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv); cudaFree(w.pl_hi); cudaFree(w.pl_lo);
+        cudaFree(w.o_hi); cudaFree(w.o_lo); cudaFree(w.h_hi); cudaFree(w.h_lo);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int pi = 0; pi < PAFUSE_MAX_PARTS; ++pi) {
+        if (ctx->side[pi]) cudaStreamDestroy(ctx->side[pi]);
+        if (ctx->ev_join[pi]) cudaEventDestroy(ctx->ev_join[pi]);
+    }
     cudaFree(ctx->flip_perm_dev); cudaFree(ctx->conn_dev); cudaFree(ctx->conn_rows_dev); cudaFree(ctx->pred);
     delete ctx;
 }
@@ -716,7 +822,7 @@ int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable) {
 int pafuse_set_debug_simt_attention(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->debug_simt_attn = enable != 0;
-    ctx->ws.rows_x_c = 0;        // the fp32 qkv buffer exists only in debug mode: force a re-allocation
+    ctx->ws[0].rows_x_c = 0;     // the fp32 qkv buffer exists only in debug mode: force a re-allocation
     return 0;
 }
 
@@ -733,6 +839,22 @@ int pafuse_set_gemm_cta_group(int32_t cta_group) {
 int pafuse_set_fuse_layernorm(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->fuse_ln = enable != 0;
+    return 0;
+}
+
+int pafuse_set_part_streams(pafuse_ctx* ctx, int32_t enable, const int32_t* shares) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    ctx->part_streams = enable != 0;
+    if (shares) {
+        for (int pi = 0; pi < ctx->num_parts; ++pi) {
+            if (shares[pi] < 2) {
+                set_last_error("pafuse_set_part_streams: a share needs at least 2 SMs (part %d: %d)", pi, shares[pi]);
+                return PAFUSE_E_ARG;
+            }
+            ctx->sm_share[pi] = shares[pi] / 2 * 2;
+        }
+        ctx->shares_fixed = true;
+    }
     return 0;
 }
 
@@ -802,8 +924,10 @@ int pafuse_linear(pafuse_ctx* ctx, const float* x, const float* w, const float* 
     if (dev_alloc(&xh, nx) || dev_alloc(&xl, nx) || dev_alloc(&wh, nw) || dev_alloc(&wl, nw)) rc = PAFUSE_E_CUDA;
     if (!rc && epilogue == EPI_GELU_SPLIT && (dev_alloc(&yh, ny) || dev_alloc(&yl, ny))) rc = PAFUSE_E_CUDA;
     if (!rc) {
-        split_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(x, xh, xl, nx, 1.0f);
+        // weights first: the GEMM may fetch its W slice ahead of its grid-dependency wait, which only covers the
+        // kernel launched immediately before it
         split_rows_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, wh, wl, nw, WEIGHT_SCALE);
+        split_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(x, xh, xl, nx, 1.0f);
         GemmArgs g;
         g.a_hi = xh; g.a_lo = xl; g.w_hi = wh; g.w_lo = wl; g.bias = b; g.out_f32 = y; g.out_hi = yh; g.out_lo = yl;
         g.M = M; g.N = N; g.K = K; g.epilogue = epilogue;
@@ -879,8 +1003,8 @@ int pafuse_qkv_attention(pafuse_ctx* ctx, const float* x, const float* w, const 
         rc = PAFUSE_E_CUDA;
     if (!rc) rc = launch_pack_qkv(w, b, wp, bp, C, hd, hds, st);
     if (!rc) {
+        split_rows_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(wp, wh, wl, nw, WEIGHT_SCALE);   // weights first, see pafuse_linear
         split_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, xh, xl, n, 1.0f);
-        split_rows_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(wp, wh, wl, nw, WEIGHT_SCALE);
         GemmArgs g;
         g.a_hi = xh; g.a_lo = xl; g.w_hi = wh; g.w_lo = wl; g.bias = bp; g.out_f32 = nullptr; g.out_hi = g.out_lo = nullptr;
         g.M = M; g.N = 24 * hds; g.K = C; g.epilogue = EPI_PLANES;

@@ -176,6 +176,23 @@ def test_layernorm_fused_in_gemm_epilogue_equals_separate_launches():
     _check_pose(b, c["golden"]["out"])
 
 
+@pytest.mark.parametrize("shares", [None, (20, 96, 32), (2, 2, 2)])
+def test_parts_side_by_side_equal_parts_in_turn(shares):
+    """The part denoisers on their own streams and SM shares (opt-in) against one after the other on the
+    caller's stream: every tile is computed by the same code in the same order, so the result is bit-identical,
+    whatever the shares."""
+    from pafuse_testlib import build_case
+    c = build_case("small_B2_H2_K3")
+    side = _model(c)
+    side.native_context().set_part_streams(True, shares)
+    turn = _model(c)
+    turn.native_context().set_part_streams(False)
+    a = side(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
+    b = turn(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
+    assert torch.equal(a, b)
+    _check_pose(a, c["golden"]["out"])
+
+
 @pytest.mark.parametrize("max_seqs", [1, 3])
 def test_workspace_chunking_is_invisible(max_seqs):
     """max_seqs smaller than the sequence count must not change the result.  Rows are independent, but the
