@@ -29,6 +29,25 @@ FLOP_PER_FORWARD_R1 = 69_384_706_048          # one pred_parts call at R=1 (SURV
 FRAMES = 27
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the one JSON line: file descriptor 1 is pointed at stderr for everything else (NCCL prints
+    its version banner to fd 1 from C, whatever NCCL_DEBUG_FILE says)."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def flops_per_frame(H, K, flip=True):
     return FLOP_PER_FORWARD_R1 * (2 if flip else 1) * H * K / FRAMES
 
@@ -155,7 +174,7 @@ def run_reference_arm(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args):
@@ -306,7 +325,7 @@ def run_ours(args):
                                 "kind": "port", "sample": f"{args.cpu_clips} clip(s) of the {Bl}-clip batch, H={H} K={K}, "
                                                           f"one pass ({sec:.1f} s)"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -324,6 +343,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-seqs", type=int, default=0, help="sequences per workspace pass (0 = library default)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
