@@ -176,6 +176,9 @@ int pafuse_set_debug_simt_attention(pafuse_ctx* ctx, int32_t enable);
 /* 1 (default): the LayerNorms that follow the proj / fc2 GEMMs are computed in their epilogues for parts whose
  * channel width fits one output tile (C <= 256); 0: separate LayerNorm launches everywhere */
 int pafuse_set_fuse_layernorm(pafuse_ctx* ctx, int32_t enable);
+/* 1: Mlp.forward (mixste.py:37-43) of the parts with C <= 256 runs as ONE kernel (fc1 + GELU + fc2 + residual +
+ * the following LayerNorms), the hidden activations staying in tensor memory; 0: fc1 and fc2 GEMM launches */
+int pafuse_set_fuse_mlp(pafuse_ctx* ctx, int32_t enable);
 /* 1: the part denoisers (body / face / hands, independent until the DDIM update: diffusionpose.py:163-172) run
  * side by side, each on its own stream and on a share of the SMs, so that the DRAM-bound kernels of one part
  * overlap the tensor-bound kernels of another; 0 (default; the overlap measured neutral on power-capped B200s):

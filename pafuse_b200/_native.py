@@ -60,6 +60,7 @@ _SIGNATURES = {
     "pafuse_set_gemm_weight_stationary": (c_int32, [c_int32]),
     "pafuse_set_fuse_layernorm": (c_int32, [c_void_p, c_int32]),
     "pafuse_set_part_streams": (c_int32, [c_void_p, c_int32, c_void_p]),
+    "pafuse_set_fuse_mlp": (c_int32, [c_void_p, c_int32]),
     "pafuse_set_debug_simt_attention": (c_int32, [c_void_p, c_int32]),
 }
 
@@ -327,6 +328,9 @@ class NativeContext:
 
     def set_fuse_layernorm(self, enable: bool):
         check(self.lib.pafuse_set_fuse_layernorm(self.handle, 1 if enable else 0), "pafuse_set_fuse_layernorm")
+
+    def set_fuse_mlp(self, enable: bool):
+        check(self.lib.pafuse_set_fuse_mlp(self.handle, 1 if enable else 0), "pafuse_set_fuse_mlp")
 
     def set_part_streams(self, enable: bool, shares=None):
         arr = None

@@ -672,6 +672,315 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     }
 }
 
+
+// ====================================================================================================
+// Fused MLP (mixste.py:37-43 + the residual add and LayerNorms of EPI_RESID_LN):
+//     x <- x + fc2(GELU(fc1(a)))  [+ the norms that follow],  a = fp16 hi/lo LayerNorm output, C <= 256.
+// The hidden activations [M, 2C] never leave the SM: per 64-column hidden chunk j
+//     acc1 = a W1[j]^T            (G1: A from shared memory, resident for the whole 256-row tile)
+//     h    = GELU(acc1 + b1)      (epilogue warps: TMEM -> registers -> fp16 hi/lo -> TMEM)
+//     acc2 += h W2[:, j]^T        (G2: A operand read from tensor memory, like P in the attention kernel)
+// and the EPI_RESID_LN epilogue runs on acc2.  Against the fc1 + fc2 launches this removes the write and the
+// read of h (16 of the 32 bytes per element-row the MLP moved through DRAM) and one launch.
+// Tensor memory (512 columns): acc2 [0, C), acc1 double-buffered at 256 / 320, h (hi 32 + lo 32 columns of packed
+// fp16 pairs) double-buffered at 384 / 448.  Shared memory: the A tile (C/64 boxes x hi/lo x 16 KB), a ring of
+// 16 KB weight stages (W1: two 64-wide K boxes of this CTA's 32 hidden rows, hi + lo; W2: 32 K columns of this
+// CTA's C/2 output rows, hi + lo), the epilogue staging boxes.
+// Issue order per tile (one thread of the even CTA): G1(0) G1(1) | G1(j+2) G2(j) ... | G2(n-2) G2(n-1), so that
+// the tensor pipe works on G1(j+2) while the epilogue warps turn chunk j into h, and the next tile's first two
+// G1s run during the LayerNorm epilogue.
+constexpr int MLP_HC = 64;                       // hidden columns per chunk
+constexpr int MLP_STAGE_BYTES = 16384;
+constexpr int MLP_A_BOX_BYTES = BM * BKW * 2;    // 16 KB: 128 rows x 64 fp16
+constexpr int MLP_TM_ACC1 = 256, MLP_TM_H = 384;
+
+struct MlpParams {
+    long long M;
+    int C, nch;                      // channels, hidden chunks (2C / 64)
+    int m_tiles;                     // tiles of 256 rows
+    int stages;                      // weight ring depth
+    int kb;                          // 64-wide K boxes of the A tile = ceil(C / 64)
+    float out_scale;
+    const float* bias1;              // [2C]
+    KernelParams ep;                 // the EPI_RESID_LN epilogue's view: N = C, bias = b2, ln
+};
+
+// D[tmem] (+)= A[tmem] * B[smem desc], CTA pair
+__device__ __forceinline__ void umma_f16_ts2(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t r[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
+                 const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
+                 const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_o_hi,
+                 const __grid_constant__ CUtensorMap tm_o_lo, const MlpParams p) {
+    constexpr int CG = 2;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ float ln_xch[128 * 2];
+    __shared__ __align__(8) uint64_t w_full[MAX_STAGES], w_empty[MAX_STAGES];
+    __shared__ __align__(8) uint64_t a_full, a_empty, acc2_full, acc2_empty;
+    __shared__ __align__(8) uint64_t acc1_full[2], acc1_empty[2], h_full[2], h_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;                                           // [kb][hi, lo][128 rows x 128 B]
+    uint8_t* smem_w = smem_a + (size_t)p.kb * 2 * MLP_A_BOX_BYTES;    // weight stage ring
+    uint8_t* smem_box = smem_w + (size_t)p.stages * MLP_STAGE_BYTES;  // epilogue staging, 4 KB per warp
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int C = p.C, nch = p.nch;
+    const int pair = (int)blockIdx.x / CG, num_pairs = (int)gridDim.x / CG;
+    const int n_local = pair < p.m_tiles ? (p.m_tiles - pair + num_pairs - 1) / num_pairs : 0;
+    const int w1_stages = (p.kb + 1) / 2;                             // W1 stages per chunk (two K boxes each)
+    const int w2_rows = C / CG;                                       // output rows of W2 this CTA loads
+
+    pdl_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tm_a_hi); prefetch_tensormap(&tm_a_lo);
+        prefetch_tensormap(&tm_w1_hi); prefetch_tensormap(&tm_w1_lo);
+        prefetch_tensormap(&tm_w2_hi); prefetch_tensormap(&tm_w2_lo);
+        prefetch_tensormap(&tm_x); prefetch_tensormap(&tm_o_hi); prefetch_tensormap(&tm_o_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&w_full[s], 1);                                 // the leader's arrive.expect_tx
+            mbar_init(&w_empty[s], 1);                                // one tcgen05.commit
+        }
+        mbar_init(&a_full, 1);
+        mbar_init(&a_empty, 1);
+        mbar_init(&acc2_full, 1);
+        mbar_init(&acc2_empty, EPI_WARPS * CG);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc1_full[b], 1);
+            mbar_init(&acc1_empty[b], EPI_WARPS * CG);                // every epilogue warp of the pair has read the chunk
+            mbar_init(&h_full[b], EPI_WARPS * CG);                    // ... has written its part of h
+            mbar_init(&h_empty[b], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<CG>(&tmem_base_slot, TMEM_COLS);
+        tmem_relinquish<CG>();
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0 && n_local > 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            auto advance = [&]() {
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            };
+            const uint32_t w2_bytes = (uint32_t)(2 * w2_rows * 64);
+            for (int i = 0; i < n_local; ++i) {
+                const int tile = pair + i * num_pairs;
+                const int m0 = (tile * CG + (int)cta_rank) * BM;
+                mbar_wait(&a_empty, (uint32_t)(i & 1) ^ 1);           // every G1 of the previous tile has retired
+                if (leader) mbar_arrive_expect_tx(&a_full, (uint32_t)(2 * p.kb * 2 * MLP_A_BOX_BYTES));
+                for (int kb = 0; kb < p.kb; ++kb) {
+                    tma_load_2d_pair(smem_a + (size_t)(2 * kb) * MLP_A_BOX_BYTES, &tm_a_hi, &a_full, kb * BKW, m0);
+                    tma_load_2d_pair(smem_a + (size_t)(2 * kb + 1) * MLP_A_BOX_BYTES, &tm_a_lo, &a_full, kb * BKW, m0);
+                }
+                for (int s = 0; s < nch + 2; ++s) {
+                    if (s < nch) {                                    // W1 of chunk s: rows 64 s + 32 rank .. + 31
+                        const int n0 = s * MLP_HC + (int)cta_rank * (MLP_HC / CG);
+                        for (int h2 = 0; h2 < w1_stages; ++h2) {
+                            const int nb = p.kb - 2 * h2 >= 2 ? 2 : 1;
+                            mbar_wait(&w_empty[stage], phase ^ 1);
+                            uint8_t* st = smem_w + (size_t)stage * MLP_STAGE_BYTES;
+                            if (leader) mbar_arrive_expect_tx(&w_full[stage], (uint32_t)(2 * nb * 2 * 4096));
+                            for (int bx = 0; bx < nb; ++bx) {
+                                tma_load_2d_pair(st + bx * 4096, &tm_w1_hi, &w_full[stage], (2 * h2 + bx) * BKW, n0);
+                                tma_load_2d_pair(st + 8192 + bx * 4096, &tm_w1_lo, &w_full[stage], (2 * h2 + bx) * BKW, n0);
+                            }
+                            advance();
+                        }
+                    }
+                    if (s >= 2) {                                     // W2 of chunk s - 2: K columns 64 j .. + 63, two stages
+                        const int j = s - 2;
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            mbar_wait(&w_empty[stage], phase ^ 1);
+                            uint8_t* st = smem_w + (size_t)stage * MLP_STAGE_BYTES;
+                            if (leader) mbar_arrive_expect_tx(&w_full[stage], 2 * w2_bytes);
+                            tma_load_2d_pair(st, &tm_w2_hi, &w_full[stage], j * MLP_HC + 32 * h2, (int)cta_rank * w2_rows);
+                            tma_load_2d_pair(st + 8192, &tm_w2_lo, &w_full[stage], j * MLP_HC + 32 * h2, (int)cta_rank * w2_rows);
+                            advance();
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread of the even CTA) =====================
+        if (lane == 0 && leader && n_local > 0) {
+            const uint32_t idesc1 = make_idesc_f16((uint32_t)(BM * CG), (uint32_t)MLP_HC);
+            const uint32_t idesc2 = make_idesc_f16((uint32_t)(BM * CG), (uint32_t)C);
+            const uint32_t sa = smem_u32(smem_a), sw = smem_u32(smem_w);
+            const uint32_t d_acc2 = tmem_base;
+            int stage = 0;
+            uint32_t phase = 0;
+            auto advance = [&]() {
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            };
+            uint32_t g1 = 0, g2 = 0;                                  // chunks issued so far (buffer = count & 1)
+            for (int i = 0; i < n_local; ++i) {
+                mbar_wait(&a_full, (uint32_t)(i & 1));                // the A tile landed (in both CTAs)
+                tcgen05_fence_after();
+                for (int s = 0; s < nch + 2; ++s) {
+                    if (s < nch) {
+                        // ---- G1(s): acc1[b] = A W1[s]^T
+                        const uint32_t b = g1 & 1u, use = g1 >> 1;
+                        mbar_wait(&acc1_empty[b], (use & 1u) ^ 1u);   // the epilogue warps have read chunk g1 - 2
+                        tcgen05_fence_after();
+                        const uint32_t d = tmem_base + (uint32_t)MLP_TM_ACC1 + b * (uint32_t)MLP_HC;
+                        for (int h2 = 0; h2 < w1_stages; ++h2) {
+                            const int nb = p.kb - 2 * h2 >= 2 ? 2 : 1;
+                            mbar_wait(&w_full[stage], phase);
+                            tcgen05_fence_after();
+                            const uint32_t st = sw + (uint32_t)stage * MLP_STAGE_BYTES;
+                            for (int bx = 0; bx < nb; ++bx) {
+                                const int kb = 2 * h2 + bx;
+                                const int k_left = C - kb * BKW;
+                                const int nk = k_left >= BKW ? BKW / UK : (k_left + UK - 1) / UK;
+                                const uint32_t a_hi = sa + (uint32_t)(2 * kb) * MLP_A_BOX_BYTES, a_lo = a_hi + MLP_A_BOX_BYTES;
+                                const uint32_t w_hi = st + (uint32_t)bx * 4096u, w_lo = w_hi + 8192u;
+                                for (int k = 0; k < nk; ++k) {
+                                    const uint32_t koff = (uint32_t)k * UK * 2;
+                                    const uint64_t dah = make_smem_desc_sw128(a_hi + koff), dal = make_smem_desc_sw128(a_lo + koff);
+                                    const uint64_t dwh = make_smem_desc_sw128(w_hi + koff), dwl = make_smem_desc_sw128(w_lo + koff);
+                                    umma_f16_ss<CG>(d, dal, dwh, idesc1, (kb | k) != 0 ? 1u : 0u);
+                                    umma_f16_ss<CG>(d, dah, dwl, idesc1, 1u);
+                                    umma_f16_ss<CG>(d, dah, dwh, idesc1, 1u);
+                                }
+                            }
+                            umma_commit<CG>(&w_empty[stage]);
+                            advance();
+                        }
+                        umma_commit<CG>(&acc1_full[b]);
+                        if (s == nch - 1) umma_commit<CG>(&a_empty);  // the A tile may be overwritten
+                        ++g1;
+                    }
+                    if (s >= 2) {
+                        // ---- G2(j): acc2 += h[b] W2[:, j]^T, h read from tensor memory
+                        const int j = s - 2;
+                        const uint32_t b = g2 & 1u, use = g2 >> 1;
+                        mbar_wait(&h_full[b], use & 1u);              // h of this chunk is in tensor memory (both CTAs)
+                        if (j == 0) mbar_wait(&acc2_empty, (uint32_t)(i & 1) ^ 1u);   // the previous tile's epilogue is done with acc2
+                        tcgen05_fence_after();
+                        const uint32_t h_hi = tmem_base + (uint32_t)MLP_TM_H + b * 64u, h_lo = h_hi + 32u;
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            mbar_wait(&w_full[stage], phase);
+                            tcgen05_fence_after();
+                            const uint32_t st = sw + (uint32_t)stage * MLP_STAGE_BYTES;
+                            for (int k = 0; k < 2; ++k) {
+                                const uint32_t kk = (uint32_t)(2 * h2 + k);                  // 16-wide K step inside the chunk
+                                const uint64_t dwh = make_smem_desc(st + (uint32_t)k * 32u, 512u, 4u);          // 64-byte swizzle
+                                const uint64_t dwl = make_smem_desc(st + 8192u + (uint32_t)k * 32u, 512u, 4u);
+                                umma_f16_ts2(d_acc2, h_lo + 8u * kk, dwh, idesc2, (j | (int)kk) != 0 ? 1u : 0u);
+                                umma_f16_ts2(d_acc2, h_hi + 8u * kk, dwl, idesc2, 1u);
+                                umma_f16_ts2(d_acc2, h_hi + 8u * kk, dwh, idesc2, 1u);
+                            }
+                            umma_commit<CG>(&w_empty[stage]);
+                            advance();
+                        }
+                        umma_commit<CG>(&h_empty[b]);
+                        if (j == nch - 1) umma_commit<CG>(&acc2_full);
+                        ++g2;
+                    }
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue warps: GELU per chunk, then residual + LayerNorms per tile =====================
+        const int q = warp & 3;                                       // TMEM lane quarter == warp % 4
+        const int half = (warp - EPI_WARP0) >> 2;                     // which 32 of the chunk's 64 columns
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const float oscale = p.out_scale;
+        uint8_t* box = smem_box + (warp - EPI_WARP0) * STG_WARP_BYTES;
+        uint32_t g = 0;
+        for (int i = 0; i < n_local; ++i) {
+            const int tile = pair + i * num_pairs;
+            const int row0 = (tile * CG + (int)cta_rank) * BM + q * 32;
+            for (int j = 0; j < nch; ++j, ++g) {
+                const uint32_t b = g & 1u, use = g >> 1;
+                uint32_t r[32];
+                float4 bv[8];
+                mbar_wait(&acc1_full[b], use & 1u);
+                tcgen05_fence_after();
+                tmem_ld_32x32(tmem_base + lane_sel + (uint32_t)MLP_TM_ACC1 + b * (uint32_t)MLP_HC + (uint32_t)half * 32u, r);
+                load_vec32(bv, p.bias1 + j * MLP_HC + half * 32);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&acc1_empty[b], 0);   // acc1[b] may take G1 of chunk g + 2
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float v0 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 0]), oscale, bv[e].x));
+                    const float v1 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 1]), oscale, bv[e].y));
+                    const float v2 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 2]), oscale, bv[e].z));
+                    const float v3 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 3]), oscale, bv[e].w));
+                    split_pair_sat(v0, v1, hi[2 * e], lo[2 * e]);
+                    split_pair_sat(v2, v3, hi[2 * e + 1], lo[2 * e + 1]);
+                }
+                mbar_wait(&h_empty[b], (use & 1u) ^ 1u);              // G2 of chunk g - 2 has read h[b]
+                tcgen05_fence_after();
+                const uint32_t h_addr = tmem_base + lane_sel + (uint32_t)MLP_TM_H + b * 64u + (uint32_t)half * 16u;
+                tmem_st_32x16(h_addr, hi);
+                tmem_st_32x16(h_addr + 32u, lo);
+                tmem_st_wait_all();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&h_full[b], 0);
+            }
+            float4 xr[8];
+            ln_fetch_x(p.ep, xr, row0, half * 32, lane);              // in flight while the last G2 finishes
+            mbar_wait(&acc2_full, (uint32_t)(i & 1));
+            tcgen05_fence_after();
+            epilogue_resid_ln<CG>(p.ep, tm_x, tm_o_hi, tm_o_lo, box, ln_xch, tmem_base + lane_sel, row0, q, half, lane, C,
+                                  oscale, &acc2_empty, xr);
+        }
+        if (lane == 0) bulk_wait_group<0>();
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
@@ -858,6 +1167,79 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     set_last_error("gemm: bad epilogue %d", g.epilogue);
     return -1;
 }
+
+
+int launch_mlp(const MlpArgs& g, cudaStream_t st) {
+    const int C = g.C, hidden = 2 * C;
+    if (!mlp_can_fuse(C) || !g.x || !g.out_hi || !g.out_lo || !g.ln.g1 || !g.ln.b1 || (g.ln.g0 && !g.ln.b0) || g.ln.x != g.x) {
+        set_last_error("mlp_fused: needs C %% 32 == 0, 64 <= C <= 256, the residual stream and the norm parameters (C=%d)", C);
+        return -1;
+    }
+    MlpParams mp;
+    mp.M = g.M;
+    mp.C = C;
+    mp.nch = hidden / MLP_HC;
+    mp.m_tiles = (int)((g.M + 2 * BM - 1) / (2 * BM));
+    mp.kb = (C + BKW - 1) / BKW;
+    mp.out_scale = g.out_scale;
+    mp.bias1 = g.b1;
+    mp.ep = KernelParams();
+    mp.ep.M = g.M;
+    mp.ep.N = C;
+    mp.ep.K = hidden;
+    mp.ep.block_n = C;
+    mp.ep.out_scale = g.out_scale;
+    mp.ep.bias = g.b2;
+    mp.ep.ln = g.ln;
+
+    auto kern = mlp_fused_kernel;
+    static int max_dyn = 0;
+    if (!max_dyn) {
+        cudaFuncAttributes fa;
+        PAFUSE_CUDA_OK(cudaFuncGetAttributes(&fa, kern));
+        max_dyn = SMEM_LIMIT - (int)fa.sharedSizeBytes;
+        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+    }
+    const int fixed = 1024 + mp.kb * 2 * MLP_A_BOX_BYTES + STG_BYTES;
+    int stages = (max_dyn - fixed) / MLP_STAGE_BYTES;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 3) {
+        set_last_error("mlp_fused: C=%d leaves room for %d weight stages only", C, stages);
+        return -1;
+    }
+    mp.stages = stages;
+    const int smem = fixed + stages * MLP_STAGE_BYTES;
+
+    CUtensorMap ah, al, w1h, w1l, w2h, w2l, ox, oh, ol;
+    if (int rc = make_map_f16(&ah, g.a_hi, g.M, C, BM)) return rc;
+    if (int rc = make_map_f16(&al, g.a_lo, g.M, C, BM)) return rc;
+    if (int rc = make_map_f16(&w1h, g.w1_hi, hidden, C, MLP_HC / 2)) return rc;
+    if (int rc = make_map_f16(&w1l, g.w1_lo, hidden, C, MLP_HC / 2)) return rc;
+    if (int rc = make_map_f16(&w2h, g.w2_hi, C, hidden, C / 2, 32)) return rc;
+    if (int rc = make_map_f16(&w2l, g.w2_lo, C, hidden, C / 2, 32)) return rc;
+    if (int rc = make_map_out(&ox, g.x, g.M, C, true)) return rc;
+    if (int rc = make_map_out(&oh, g.out_hi, g.M, C, false)) return rc;
+    if (int rc = make_map_out(&ol, g.out_lo, g.M, C, false)) return rc;
+    const int sms = g.sm_limit > 0 && g.sm_limit < g_num_sms ? g.sm_limit : g_num_sms;
+    const int max_pairs = sms / 2 > 0 ? sms / 2 : 1;
+    const int grid = 2 * (mp.m_tiles < max_pairs ? mp.m_tiles : max_pairs);
+    PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(NUM_THREADS), (size_t)smem, st, 2, ah, al, w1h, w1l, w2h, w2l,
+                                ox, oh, ol, mp));
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace
+
+bool mlp_can_fuse(int C) { return C % 32 == 0 && C >= 64 && C <= 256; }
+
+int launch_mlp_fused(const MlpArgs& g, cudaStream_t st) {
+    if (g.M == 0) return 0;
+    if (int rc = gemm_init()) return rc;
+    return launch_mlp(g, st);
+}
+
+namespace {
 
 }  // namespace
 

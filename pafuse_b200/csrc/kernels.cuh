@@ -127,6 +127,24 @@ struct GemmArgs {
     int sm_limit = 0;                   // > 0: use at most this many SMs (the parts run side by side on SM shares)
 };
 
+// Fused MLP of a block (see mlp_fused_kernel): x <- x + fc2(GELU(fc1(a))) and the LayerNorms of EPI_RESID_LN
+struct MlpArgs {
+    const op_t *a_hi, *a_lo;   // [M,C]   norm2 output
+    const op_t *w1_hi, *w1_lo; // [2C,C]  fc1 weight
+    const float* b1;           // [2C]
+    const op_t *w2_hi, *w2_lo; // [C,2C]  fc2 weight
+    const float* b2;           // [C]
+    float* x;                  // [M,C]   residual stream, updated in place (== ln.x)
+    op_t *out_hi, *out_lo;     // [M,C]   LayerNorm output for the next GEMM
+    long long M;
+    int C;
+    float out_scale = WEIGHT_UNSCALE;
+    GemmLnFuse ln;
+    int sm_limit = 0;
+};
+bool mlp_can_fuse(int C);
+int launch_mlp_fused(const MlpArgs& g, cudaStream_t st);
+
 int launch_split_weights(const float* w, op_t* hi, op_t* lo, size_t n, cudaStream_t st);
 int launch_time_mlp(const float* sinus, const float* w1, const float* b1, const float* w2, const float* b2,
                     float* temb, int C, cudaStream_t st);

@@ -125,6 +125,7 @@ struct pafuse_ctx {
     bool debug_simt = false;
     bool debug_simt_attn = false;
     bool fuse_ln = true;             // LayerNorms fused into the proj / fc2 GEMM epilogues where the row fits one tile
+    bool fuse_mlp = false;           // fc1 + GELU + fc2 (+ those LayerNorms) in one kernel for the same parts
     Profiler prof;
 };
 
@@ -334,7 +335,7 @@ int run_part(pafuse_ctx* ctx, int pi, Workspace& w, const float* x2d, const floa
 
         // proj: x += o W^T + b, then norm2 -> hi/lo
         g = GemmArgs();
-        g.M = M;
+        g.M = M; g.sm_limit = sm_limit;
         g.a_hi = w.o_hi; g.a_lo = w.o_lo;
         g.w_hi = p.wh(b + "attn.proj.weight"); g.w_lo = p.wl(b + "attn.proj.weight");
         g.bias = p.w(b + "attn.proj.bias");
@@ -354,8 +355,29 @@ int run_part(pafuse_ctx* ctx, int pi, Workspace& w, const float* x2d, const floa
             if (int rc = launch_ln_chain(l, st)) return rc;
         }
 
+        if (fuse && ctx->fuse_mlp && blk + 1 < nblk && mlp_can_fuse(C)) {
+            // fc1 + GELU + fc2 + residual + the norms that follow in ONE kernel: h stays in tensor memory
+            const bool tnext = (blk + 1) & 1;
+            const std::string bn = std::string(tnext ? "TTEblocks." : "STEblocks.") + std::to_string((blk + 1) / 2) + ".";
+            const char* sn = temporal ? "Temporal_norm" : "Spatial_norm";       // norm that closes this block
+            MlpArgs m;
+            m.a_hi = w.a_hi; m.a_lo = w.a_lo;
+            m.w1_hi = p.wh(b + "mlp.fc1.weight"); m.w1_lo = p.wl(b + "mlp.fc1.weight"); m.b1 = p.w(b + "mlp.fc1.bias");
+            m.w2_hi = p.wh(b + "mlp.fc2.weight"); m.w2_lo = p.wl(b + "mlp.fc2.weight"); m.b2 = p.w(b + "mlp.fc2.bias");
+            m.x = w.x; m.out_hi = w.a_hi; m.out_lo = w.a_lo;
+            m.M = M; m.C = C; m.sm_limit = sm_limit;
+            m.ln.x = w.x;
+            m.ln.g0 = p.w(std::string(sn) + ".weight"); m.ln.b0 = p.w(std::string(sn) + ".bias"); m.ln.eps0 = 1e-6f;
+            if (blk == 0) m.ln.add_f = p.w("Temporal_pos_embed");
+            m.ln.g1 = p.w(bn + "norm1.weight"); m.ln.b1 = p.w(bn + "norm1.bias"); m.ln.eps1 = 1e-6f;
+            m.ln.J = J; m.ln.F = F;
+            ProfScope ps(ctx, CAT_GEMM, 2.0 * 2.0 * (double)M * C * 2 * C, st);
+            if (int rc = launch_mlp_fused(m, st)) return rc;
+            continue;
+        }
+
         g = GemmArgs();
-        g.M = M;
+        g.M = M; g.sm_limit = sm_limit;
         g.a_hi = w.a_hi; g.a_lo = w.a_lo;
         g.w_hi = p.wh(b + "mlp.fc1.weight"); g.w_lo = p.wl(b + "mlp.fc1.weight");
         g.bias = p.w(b + "mlp.fc1.bias");
@@ -366,7 +388,7 @@ int run_part(pafuse_ctx* ctx, int pi, Workspace& w, const float* x2d, const floa
         // fc2: x += h W^T + b; fused: the norm that closes this block (+ Temporal_pos_embed after STE 0) and
         // norm1 of the next block
         g = GemmArgs();
-        g.M = M;
+        g.M = M; g.sm_limit = sm_limit;
         g.a_hi = w.h_hi; g.a_lo = w.h_lo;
         g.w_hi = p.wh(b + "mlp.fc2.weight"); g.w_lo = p.wl(b + "mlp.fc2.weight");
         g.bias = p.w(b + "mlp.fc2.bias");
@@ -577,6 +599,7 @@ int pafuse_create(const pafuse_config* cfg, pafuse_ctx** out) {
     if (int rc = gemm_init()) return rc;
     if (const char* e = getenv("PAFUSE_FUSE_LN")) ctx->fuse_ln = atoi(e) != 0;
     if (const char* e = getenv("PAFUSE_PART_STREAMS")) ctx->part_streams = atoi(e) != 0;
+    if (const char* e = getenv("PAFUSE_FUSE_MLP")) ctx->fuse_mlp = atoi(e) != 0;
     *out = ctx;
     return 0;
 }
@@ -839,6 +862,12 @@ int pafuse_set_gemm_cta_group(int32_t cta_group) {
 int pafuse_set_fuse_layernorm(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->fuse_ln = enable != 0;
+    return 0;
+}
+
+int pafuse_set_fuse_mlp(pafuse_ctx* ctx, int32_t enable) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    ctx->fuse_mlp = enable != 0;
     return 0;
 }
 

@@ -1,0 +1,61 @@
+"""Precision experiment on the CPU oracle (not a test, not collected): see DESIGN.md section 10."""
+import sys, torch, torch.nn.functional as Fn
+import os; sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..'))
+from oracle import pafuse_oracle as orc
+from pafuse_b200 import synthetic
+from pafuse_b200.h3wb import H3WBSkeleton, merged_part_indices
+torch.set_num_threads(8)
+MODE = 'exact'
+def f8(x, s):
+    return (x * s).to(torch.float8_e4m3fn).float() / s
+def pow2scale(x, target=64.0):
+    m = x.abs().max().clamp_min(1e-30)
+    return 2.0 ** torch.floor(torch.log2(target / m))
+def lin(x, w, b):
+    if MODE == 'exact':
+        return Fn.linear(x, w, b)
+    xh = x.half().float(); xl = x - xh
+    wh = w.half().float(); wl = w - wh
+    if MODE == 'f16x3':
+        return xh @ wh.t() + (xl.half().float() @ wh.t()) + (xh @ wl.half().float().t()) + b
+    if MODE == 'f16x1':
+        return xh @ wh.t() + b
+    # fp8 corrections
+    sxl, swh, sxh, swl = pow2scale(xl), pow2scale(wh), pow2scale(xh), pow2scale(wl)
+    c1 = f8(xl, sxl) @ f8(wh, swh).t()
+    c2 = f8(xh, sxh) @ f8(wl, swl).t()
+    return xh @ wh.t() + c1 + c2 + b
+def _attention(w, pre, x, heads):
+    G, L, C = x.shape
+    hd = C // heads
+    qkv = lin(x, w[pre + "attn.qkv.weight"], w[pre + "attn.qkv.bias"])
+    qkv = qkv.reshape(G, L, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    a = (q @ k.transpose(-2, -1)) * (hd ** -0.5)
+    a = a.softmax(dim=-1)
+    o = (a @ v).transpose(1, 2).reshape(G, L, C)
+    return lin(o, w[pre + "attn.proj.weight"], w[pre + "attn.proj.bias"])
+def _block(w, pre, x, heads):
+    C = x.shape[-1]
+    x = x + _attention(w, pre, Fn.layer_norm(x, (C,), w[pre + "norm1.weight"], w[pre + "norm1.bias"], 1e-6), heads)
+    h = Fn.layer_norm(x, (C,), w[pre + "norm2.weight"], w[pre + "norm2.bias"], 1e-6)
+    h = Fn.gelu(lin(h, w[pre + "mlp.fc1.weight"], w[pre + "mlp.fc1.bias"]))
+    return x + lin(h, w[pre + "mlp.fc2.weight"], w[pre + "mlp.fc2.bias"])
+orc._attention = _attention; orc._block = _block
+B, H, K, depth = 1, 5, 5, 8
+sk = H3WBSkeleton()
+sd = synthetic.synthetic_state_dict(seed=1, depth=depth)
+x2d, x2df = synthetic.synthetic_inputs(B, seed=1)
+noises = synthetic.synthetic_noise(B, H, K, seed=1)
+parts = merged_part_indices(sk.parts_joint_indices)
+def run(mode):
+    global MODE
+    MODE = mode
+    return orc.ddim_sample_flip(sd, parts, x2d, x2df, noises, sk.joints_left, sk.joints_right, H, K, depth=depth)
+with torch.no_grad():
+    ref = run('exact')
+    for m in ['f16x3', 'fp8corr', 'f16x1']:
+        out = run(m)
+        d = out - ref
+        viol = (d.abs() > 1e-3 * ref.abs() + 2e-5).float().mean().item()
+        print(m, 'mpjpe mm %.5f' % (d.norm(dim=-1).mean().item()*1e3), 'maxabs %.2e' % d.abs().max().item(), 'tol-violations %.2e' % viol, flush=True)

@@ -176,6 +176,21 @@ def test_layernorm_fused_in_gemm_epilogue_equals_separate_launches():
     _check_pose(b, c["golden"]["out"])
 
 
+def test_mlp_fused_in_one_kernel_equals_fc1_fc2_launches():
+    """fc1 + GELU + fc2 + residual + LayerNorms as one kernel (face, hands; hidden activations in tensor memory)
+    against the two GEMM launches: the same MMAs in the same order on the same operands."""
+    from pafuse_testlib import build_case
+    c = build_case("small_B2_H2_K3")
+    fused = _model(c)
+    fused.native_context().set_fuse_mlp(True)
+    plain = _model(c)
+    plain.native_context().set_fuse_mlp(False)
+    a = fused(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
+    b = plain(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
+    assert (a - b).abs().max().item() < 2e-5
+    _check_pose(a, c["golden"]["out"])
+
+
 @pytest.mark.parametrize("shares", [None, (20, 96, 32), (2, 2, 2)])
 def test_parts_side_by_side_equal_parts_in_turn(shares):
     """The part denoisers on their own streams and SM shares (opt-in) against one after the other on the
