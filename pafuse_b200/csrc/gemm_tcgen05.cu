@@ -158,6 +158,8 @@ __device__ __forceinline__ void load_vec32(float4 (&v)[8], const float* src) {
     for (int i = 0; i < 8; ++i) v[i] = __ldg(s4 + i);
 }
 
+// (A bulk L2 prefetch of the next tile's residual rows -- they are one contiguous range of x -- was tried against the
+// x-fetch stalls of this epilogue and made proj / fc2 5-14 % slower, with 25 % more DRAM reads: profiles/r1n_*.)
 template <int CG>
 __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const CUtensorMap& tm_x, const CUtensorMap& tm_hi,
                                                   const CUtensorMap& tm_lo, uint8_t* box, float* xch, uint32_t t_base,
@@ -550,7 +552,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             walk.at(it, m_tile, n_tile);
             const int row0 = (m_tile * CG + (int)cta_rank) * BM + q * 32;   // first row of this warp's box
             float4 xr[8];                                             // EPI_RESID_LN: x of the next chunk
-            if (EPI == EPI_RESID_LN) ln_fetch_x(p, xr, row0, half * 32, lane);   // in flight while the main loop finishes
+            if (EPI == EPI_RESID_LN) {
+                ln_fetch_x(p, xr, row0, half * 32, lane);             // in flight while the main loop finishes
+            }
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
@@ -676,30 +680,34 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 // ====================================================================================================
 // Fused MLP (mixste.py:37-43 + the residual add and LayerNorms of EPI_RESID_LN):
 //     x <- x + fc2(GELU(fc1(a)))  [+ the norms that follow],  a = fp16 hi/lo LayerNorm output, C <= 256.
-// The hidden activations [M, 2C] never leave the SM: per 64-column hidden chunk j
+// The hidden activations [M, 2C] never leave the SM: per 128-column hidden chunk j
 //     acc1 = a W1[j]^T            (G1: A from shared memory, resident for the whole 256-row tile)
-//     h    = GELU(acc1 + b1)      (epilogue warps: TMEM -> registers -> fp16 hi/lo -> TMEM)
+//     h    = GELU(acc1 + b1)      (epilogue warps: TMEM -> registers -> fp16 hi/lo -> TMEM, in place over acc1)
 //     acc2 += h W2[:, j]^T        (G2: A operand read from tensor memory, like P in the attention kernel)
 // and the EPI_RESID_LN epilogue runs on acc2.  Against the fc1 + fc2 launches this removes the write and the
 // read of h (16 of the 32 bytes per element-row the MLP moved through DRAM) and one launch.
-// Tensor memory (512 columns): acc2 [0, C), acc1 double-buffered at 256 / 320, h (hi 32 + lo 32 columns of packed
-// fp16 pairs) double-buffered at 384 / 448.  Shared memory: the A tile (C/64 boxes x hi/lo x 16 KB), a ring of
-// 16 KB weight stages (W1: two 64-wide K boxes of this CTA's 32 hidden rows, hi + lo; W2: 32 K columns of this
-// CTA's C/2 output rows, hi + lo), the epilogue staging boxes.
-// Issue order per tile (one thread of the even CTA): G1(0) G1(1) | G1(j+2) G2(j) ... | G2(n-2) G2(n-1), so that
-// the tensor pipe works on G1(j+2) while the epilogue warps turn chunk j into h, and the next tile's first two
-// G1s run during the LayerNorm epilogue.
-constexpr int MLP_HC = 64;                       // hidden columns per chunk
+// Tensor memory (512 columns): acc2 [0, C); two chunk buffers of 128 columns at 256 / 384, each holding acc1 (fp32)
+// and then h (hi in the first hc/2 columns, lo in the next hc/2, packed fp16 pairs).  Shared memory: the A tile
+// (C/64 boxes x hi/lo x 16 KB), a ring of 16 KB weight stages (W1: one 64-wide K box of this CTA's 64 hidden rows,
+// hi + lo; W2: 32 K columns of this CTA's C/2 output rows, hi + lo), the epilogue staging boxes.
+// Issue order per tile (one thread of the even CTA): G1(0) G1(1) | G2(j) G1(j+2) ... | G2(n-2) G2(n-1): the tensor
+// pipe executes in issue order, so G1(j+2) overwrites a chunk buffer only after G2(j) has read h from it, and it
+// works on G1(j+1) while the epilogue warps turn chunk j into h.
+// The first version used 64-column chunks: its G1 MMAs (N = 64, 32 cycles of math) form a chain of dependent
+// accumulations into one tile and ran at the pipe's latency (~160 cycles per MMA measured, profiles/r1n_*): the
+// kernel was 20-28 % SLOWER than the two GEMM launches.
+constexpr int MLP_HC = 128;                      // hidden columns per chunk (the last chunk may be 64)
 constexpr int MLP_STAGE_BYTES = 16384;
 constexpr int MLP_A_BOX_BYTES = BM * BKW * 2;    // 16 KB: 128 rows x 64 fp16
-constexpr int MLP_TM_ACC1 = 256, MLP_TM_H = 384;
+constexpr int MLP_TM_BUF = 256;                  // chunk buffer b at MLP_TM_BUF + 128 b
 
 struct MlpParams {
     long long M;
-    int C, nch;                      // channels, hidden chunks (2C / 64)
+    int C, hidden, nch;              // channels, hidden width (2C), hidden chunks
     int m_tiles;                     // tiles of 256 rows
     int stages;                      // weight ring depth
     int kb;                          // 64-wide K boxes of the A tile = ceil(C / 64)
+    int stagger;                     // start delay, in cycles, per step of (CTA pair % 4)
     float out_scale;
     const float* bias1;              // [2C]
     KernelParams ep;                 // the EPI_RESID_LN epilogue's view: N = C, bias = b2, ln
@@ -724,6 +732,22 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t r[1
         : "memory");
 }
 
+// 32 accumulator columns -> bias + GELU -> 16 packed fp16 hi pairs and 16 lo pairs
+__device__ __forceinline__ void mlp_gelu_split32(const uint32_t (&r)[32], const float* bias, float oscale, uint32_t (&hi)[16],
+                                                 uint32_t (&lo)[16]) {
+    float4 bv[8];
+    load_vec32(bv, bias);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float v0 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 0]), oscale, bv[e].x));
+        const float v1 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 1]), oscale, bv[e].y));
+        const float v2 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 2]), oscale, bv[e].z));
+        const float v3 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 3]), oscale, bv[e].w));
+        split_pair_sat(v0, v1, hi[2 * e], lo[2 * e]);
+        split_pair_sat(v2, v3, hi[2 * e + 1], lo[2 * e + 1]);
+    }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
@@ -735,7 +759,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     __shared__ float ln_xch[128 * 2];
     __shared__ __align__(8) uint64_t w_full[MAX_STAGES], w_empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t a_full, a_empty, acc2_full, acc2_empty;
-    __shared__ __align__(8) uint64_t acc1_full[2], acc1_empty[2], h_full[2], h_empty[2];
+    __shared__ __align__(8) uint64_t acc1_full[2], h_full[2];
     __shared__ uint32_t tmem_base_slot;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -750,8 +774,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int C = p.C, nch = p.nch;
     const int pair = (int)blockIdx.x / CG, num_pairs = (int)gridDim.x / CG;
     const int n_local = pair < p.m_tiles ? (p.m_tiles - pair + num_pairs - 1) / num_pairs : 0;
-    const int w1_stages = (p.kb + 1) / 2;                             // W1 stages per chunk (two K boxes each)
     const int w2_rows = C / CG;                                       // output rows of W2 this CTA loads
+    auto chunk_width = [&](int j) { return p.hidden - j * MLP_HC >= MLP_HC ? MLP_HC : p.hidden - j * MLP_HC; };
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
@@ -771,9 +795,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         mbar_init(&acc2_empty, EPI_WARPS * CG);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc1_full[b], 1);
-            mbar_init(&acc1_empty[b], EPI_WARPS * CG);                // every epilogue warp of the pair has read the chunk
-            mbar_init(&h_full[b], EPI_WARPS * CG);                    // ... has written its part of h
-            mbar_init(&h_empty[b], 1);
+            mbar_init(&h_full[b], EPI_WARPS * CG);                    // every epilogue warp of the pair has written its part of h
         }
         fence_barrier_init();
     }
@@ -799,6 +821,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 }
             };
             const uint32_t w2_bytes = (uint32_t)(2 * w2_rows * 64);
+            // Every tile costs the same, so CTA pairs started together stay in lock-step: all of them run the
+            // DRAM-heavy LayerNorm epilogue (12 bytes per element) at the same time, DRAM saturates for that phase
+            // and idles during the chunk phases.  A one-time start offset per pair spreads the epilogues over the
+            // tile period.
+            if (p.stagger > 0 && (pair & 3) != 0) {
+                const long long t0 = clock64(), wait_for = (long long)(pair & 3) * p.stagger;
+                while (clock64() - t0 < wait_for) {
+                }
+            }
             for (int i = 0; i < n_local; ++i) {
                 const int tile = pair + i * num_pairs;
                 const int m0 = (tile * CG + (int)cta_rank) * BM;
@@ -809,28 +840,29 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     tma_load_2d_pair(smem_a + (size_t)(2 * kb + 1) * MLP_A_BOX_BYTES, &tm_a_lo, &a_full, kb * BKW, m0);
                 }
                 for (int s = 0; s < nch + 2; ++s) {
-                    if (s < nch) {                                    // W1 of chunk s: rows 64 s + 32 rank .. + 31
-                        const int n0 = s * MLP_HC + (int)cta_rank * (MLP_HC / CG);
-                        for (int h2 = 0; h2 < w1_stages; ++h2) {
-                            const int nb = p.kb - 2 * h2 >= 2 ? 2 : 1;
-                            mbar_wait(&w_empty[stage], phase ^ 1);
-                            uint8_t* st = smem_w + (size_t)stage * MLP_STAGE_BYTES;
-                            if (leader) mbar_arrive_expect_tx(&w_full[stage], (uint32_t)(2 * nb * 2 * 4096));
-                            for (int bx = 0; bx < nb; ++bx) {
-                                tma_load_2d_pair(st + bx * 4096, &tm_w1_hi, &w_full[stage], (2 * h2 + bx) * BKW, n0);
-                                tma_load_2d_pair(st + 8192 + bx * 4096, &tm_w1_lo, &w_full[stage], (2 * h2 + bx) * BKW, n0);
-                            }
-                            advance();
-                        }
-                    }
-                    if (s >= 2) {                                     // W2 of chunk s - 2: K columns 64 j .. + 63, two stages
+                    if (s >= 2) {                                     // W2 of chunk s - 2: 32 K columns per stage
                         const int j = s - 2;
-                        for (int h2 = 0; h2 < 2; ++h2) {
+                        const int nst = chunk_width(j) / 32;
+                        for (int h2 = 0; h2 < nst; ++h2) {
                             mbar_wait(&w_empty[stage], phase ^ 1);
                             uint8_t* st = smem_w + (size_t)stage * MLP_STAGE_BYTES;
                             if (leader) mbar_arrive_expect_tx(&w_full[stage], 2 * w2_bytes);
                             tma_load_2d_pair(st, &tm_w2_hi, &w_full[stage], j * MLP_HC + 32 * h2, (int)cta_rank * w2_rows);
                             tma_load_2d_pair(st + 8192, &tm_w2_lo, &w_full[stage], j * MLP_HC + 32 * h2, (int)cta_rank * w2_rows);
+                            advance();
+                        }
+                    }
+                    if (s < nch) {
+                        // W1 of chunk s: this CTA's half of the chunk's rows, one 64-wide K box per stage.  The box is
+                        // always 64 rows; a 64-column last chunk uses its first 32 (the rest is the peer's half, or
+                        // zero-fill past the tensor).
+                        const int n0 = s * MLP_HC + (int)cta_rank * (chunk_width(s) / CG);
+                        for (int kb = 0; kb < p.kb; ++kb) {
+                            mbar_wait(&w_empty[stage], phase ^ 1);
+                            uint8_t* st = smem_w + (size_t)stage * MLP_STAGE_BYTES;
+                            if (leader) mbar_arrive_expect_tx(&w_full[stage], (uint32_t)(2 * 2 * 8192));
+                            tma_load_2d_pair(st, &tm_w1_hi, &w_full[stage], kb * BKW, n0);
+                            tma_load_2d_pair(st + 8192, &tm_w1_lo, &w_full[stage], kb * BKW, n0);
                             advance();
                         }
                     }
@@ -840,10 +872,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread of the even CTA) =====================
         if (lane == 0 && leader && n_local > 0) {
-            const uint32_t idesc1 = make_idesc_f16((uint32_t)(BM * CG), (uint32_t)MLP_HC);
             const uint32_t idesc2 = make_idesc_f16((uint32_t)(BM * CG), (uint32_t)C);
             const uint32_t sa = smem_u32(smem_a), sw = smem_u32(smem_w);
             const uint32_t d_acc2 = tmem_base;
+            const uint64_t a_desc0 = make_smem_desc_sw128(sa);        // + byte offset / 16 selects box, half and K slice
             int stage = 0;
             uint32_t phase = 0;
             auto advance = [&]() {
@@ -857,30 +889,57 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 mbar_wait(&a_full, (uint32_t)(i & 1));                // the A tile landed (in both CTAs)
                 tcgen05_fence_after();
                 for (int s = 0; s < nch + 2; ++s) {
-                    if (s < nch) {
-                        // ---- G1(s): acc1[b] = A W1[s]^T
-                        const uint32_t b = g1 & 1u, use = g1 >> 1;
-                        mbar_wait(&acc1_empty[b], (use & 1u) ^ 1u);   // the epilogue warps have read chunk g1 - 2
+                    if (s >= 2) {
+                        // ---- G2(j): acc2 += h W2[:, j]^T, h read from the chunk buffer in tensor memory
+                        const int j = s - 2;
+                        const int hc = chunk_width(j);
+                        const uint32_t b = g2 & 1u, use = g2 >> 1;
+                        mbar_wait(&h_full[b], use & 1u);              // h of this chunk is in tensor memory (both CTAs)
+                        if (j == 0) mbar_wait(&acc2_empty, (uint32_t)(i & 1) ^ 1u);   // the previous tile's epilogue is done with acc2
                         tcgen05_fence_after();
-                        const uint32_t d = tmem_base + (uint32_t)MLP_TM_ACC1 + b * (uint32_t)MLP_HC;
-                        for (int h2 = 0; h2 < w1_stages; ++h2) {
-                            const int nb = p.kb - 2 * h2 >= 2 ? 2 : 1;
+                        const uint32_t h_hi = tmem_base + (uint32_t)MLP_TM_BUF + b * 128u, h_lo = h_hi + (uint32_t)(hc / 2);
+                        for (int h2 = 0; h2 < hc / 32; ++h2) {
                             mbar_wait(&w_full[stage], phase);
                             tcgen05_fence_after();
                             const uint32_t st = sw + (uint32_t)stage * MLP_STAGE_BYTES;
-                            for (int bx = 0; bx < nb; ++bx) {
-                                const int kb = 2 * h2 + bx;
-                                const int k_left = C - kb * BKW;
-                                const int nk = k_left >= BKW ? BKW / UK : (k_left + UK - 1) / UK;
-                                const uint32_t a_hi = sa + (uint32_t)(2 * kb) * MLP_A_BOX_BYTES, a_lo = a_hi + MLP_A_BOX_BYTES;
-                                const uint32_t w_hi = st + (uint32_t)bx * 4096u, w_lo = w_hi + 8192u;
-                                for (int k = 0; k < nk; ++k) {
-                                    const uint32_t koff = (uint32_t)k * UK * 2;
-                                    const uint64_t dah = make_smem_desc_sw128(a_hi + koff), dal = make_smem_desc_sw128(a_lo + koff);
-                                    const uint64_t dwh = make_smem_desc_sw128(w_hi + koff), dwl = make_smem_desc_sw128(w_lo + koff);
-                                    umma_f16_ss<CG>(d, dal, dwh, idesc1, (kb | k) != 0 ? 1u : 0u);
-                                    umma_f16_ss<CG>(d, dah, dwl, idesc1, 1u);
-                                    umma_f16_ss<CG>(d, dah, dwh, idesc1, 1u);
+                            const uint64_t dwh0 = make_smem_desc(st, 512u, 4u), dwl0 = make_smem_desc(st + 8192u, 512u, 4u);   // 64-byte swizzle
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const uint32_t kk = (uint32_t)(2 * h2 + k);                  // 16-wide K step inside the chunk
+                                const uint64_t ko = (uint64_t)(k * 2);                       // 32 bytes, in 16-byte units
+                                umma_f16_ts2(d_acc2, h_lo + 8u * kk, dwh0 + ko, idesc2, (j | (int)kk) != 0 ? 1u : 0u);
+                                umma_f16_ts2(d_acc2, h_hi + 8u * kk, dwl0 + ko, idesc2, 1u);
+                                umma_f16_ts2(d_acc2, h_hi + 8u * kk, dwh0 + ko, idesc2, 1u);
+                            }
+                            umma_commit<CG>(&w_empty[stage]);
+                            advance();
+                        }
+                        if (j == nch - 1) umma_commit<CG>(&acc2_full);
+                        ++g2;
+                    }
+                    if (s < nch) {
+                        // ---- G1(s): chunk buffer <- A W1[s]^T.  The buffer held h of chunk s - 2, whose G2 was issued
+                        // above / earlier by this thread: the tensor pipe executes in issue order.
+                        const int hc = chunk_width(s);
+                        const uint32_t idesc1 = make_idesc_f16((uint32_t)(BM * CG), (uint32_t)hc);
+                        const uint32_t b = g1 & 1u;
+                        const uint32_t d = tmem_base + (uint32_t)MLP_TM_BUF + b * 128u;
+                        for (int kb = 0; kb < p.kb; ++kb) {
+                            mbar_wait(&w_full[stage], phase);
+                            tcgen05_fence_after();
+                            const uint32_t st = sw + (uint32_t)stage * MLP_STAGE_BYTES;
+                            const int k_left = C - kb * BKW;
+                            const int nk = k_left >= BKW ? BKW / UK : (k_left + UK - 1) / UK;
+                            const uint64_t dah0 = a_desc0 + (uint64_t)((2 * kb) * (MLP_A_BOX_BYTES >> 4));
+                            const uint64_t dal0 = dah0 + (uint64_t)(MLP_A_BOX_BYTES >> 4);
+                            const uint64_t dwh0 = make_smem_desc_sw128(st), dwl0 = make_smem_desc_sw128(st + 8192u);
+#pragma unroll
+                            for (int k = 0; k < BKW / UK; ++k) {
+                                if (k < nk) {
+                                    const uint64_t ko = (uint64_t)(k * 2);                   // 32 bytes along K, in 16-byte units
+                                    umma_f16_ss<CG>(d, dal0 + ko, dwh0 + ko, idesc1, (kb | k) != 0 ? 1u : 0u);
+                                    umma_f16_ss<CG>(d, dah0 + ko, dwl0 + ko, idesc1, 1u);
+                                    umma_f16_ss<CG>(d, dah0 + ko, dwh0 + ko, idesc1, 1u);
                                 }
                             }
                             umma_commit<CG>(&w_empty[stage]);
@@ -890,40 +949,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                         if (s == nch - 1) umma_commit<CG>(&a_empty);  // the A tile may be overwritten
                         ++g1;
                     }
-                    if (s >= 2) {
-                        // ---- G2(j): acc2 += h[b] W2[:, j]^T, h read from tensor memory
-                        const int j = s - 2;
-                        const uint32_t b = g2 & 1u, use = g2 >> 1;
-                        mbar_wait(&h_full[b], use & 1u);              // h of this chunk is in tensor memory (both CTAs)
-                        if (j == 0) mbar_wait(&acc2_empty, (uint32_t)(i & 1) ^ 1u);   // the previous tile's epilogue is done with acc2
-                        tcgen05_fence_after();
-                        const uint32_t h_hi = tmem_base + (uint32_t)MLP_TM_H + b * 64u, h_lo = h_hi + 32u;
-                        for (int h2 = 0; h2 < 2; ++h2) {
-                            mbar_wait(&w_full[stage], phase);
-                            tcgen05_fence_after();
-                            const uint32_t st = sw + (uint32_t)stage * MLP_STAGE_BYTES;
-                            for (int k = 0; k < 2; ++k) {
-                                const uint32_t kk = (uint32_t)(2 * h2 + k);                  // 16-wide K step inside the chunk
-                                const uint64_t dwh = make_smem_desc(st + (uint32_t)k * 32u, 512u, 4u);          // 64-byte swizzle
-                                const uint64_t dwl = make_smem_desc(st + 8192u + (uint32_t)k * 32u, 512u, 4u);
-                                umma_f16_ts2(d_acc2, h_lo + 8u * kk, dwh, idesc2, (j | (int)kk) != 0 ? 1u : 0u);
-                                umma_f16_ts2(d_acc2, h_hi + 8u * kk, dwl, idesc2, 1u);
-                                umma_f16_ts2(d_acc2, h_hi + 8u * kk, dwh, idesc2, 1u);
-                            }
-                            umma_commit<CG>(&w_empty[stage]);
-                            advance();
-                        }
-                        umma_commit<CG>(&h_empty[b]);
-                        if (j == nch - 1) umma_commit<CG>(&acc2_full);
-                        ++g2;
-                    }
                 }
             }
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue warps: GELU per chunk, then residual + LayerNorms per tile =====================
         const int q = warp & 3;                                       // TMEM lane quarter == warp % 4
-        const int half = (warp - EPI_WARP0) >> 2;                     // which 32 of the chunk's 64 columns
+        const int half = (warp - EPI_WARP0) >> 2;                     // which half of the chunk's columns
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const float oscale = p.out_scale;
         uint8_t* box = smem_box + (warp - EPI_WARP0) * STG_WARP_BYTES;
@@ -932,32 +964,30 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             const int tile = pair + i * num_pairs;
             const int row0 = (tile * CG + (int)cta_rank) * BM + q * 32;
             for (int j = 0; j < nch; ++j, ++g) {
+                const int hc = chunk_width(j);
                 const uint32_t b = g & 1u, use = g >> 1;
-                uint32_t r[32];
-                float4 bv[8];
+                const uint32_t buf = tmem_base + lane_sel + (uint32_t)MLP_TM_BUF + b * 128u;
+                const int c_first = half * (hc / 2);                  // this warp's columns of the chunk: hc / 2 of them
+                const float* bias = p.bias1 + j * MLP_HC + c_first;
                 mbar_wait(&acc1_full[b], use & 1u);
                 tcgen05_fence_after();
-                tmem_ld_32x32(tmem_base + lane_sel + (uint32_t)MLP_TM_ACC1 + b * (uint32_t)MLP_HC + (uint32_t)half * 32u, r);
-                load_vec32(bv, p.bias1 + j * MLP_HC + half * 32);
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(buf + (uint32_t)c_first, r0);
+                if (hc == MLP_HC) tmem_ld_32x32(buf + (uint32_t)c_first + 32u, r1);
                 tmem_ld_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&acc1_empty[b], 0);   // acc1[b] may take G1 of chunk g + 2
+                // h goes over acc1 in place, and this warp's lo columns are the other warp's accumulator columns
+                // (and its hi columns ours): both warps of the lane quarter must have read before either writes
+                pair_bar_sync(1 + q);
                 uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float v0 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 0]), oscale, bv[e].x));
-                    const float v1 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 1]), oscale, bv[e].y));
-                    const float v2 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 2]), oscale, bv[e].z));
-                    const float v3 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 3]), oscale, bv[e].w));
-                    split_pair_sat(v0, v1, hi[2 * e], lo[2 * e]);
-                    split_pair_sat(v2, v3, hi[2 * e + 1], lo[2 * e + 1]);
+                const uint32_t hi_addr = buf + (uint32_t)(c_first / 2), lo_addr = hi_addr + (uint32_t)(hc / 2);
+                mlp_gelu_split32(r0, bias, oscale, hi, lo);
+                tmem_st_32x16(hi_addr, hi);
+                tmem_st_32x16(lo_addr, lo);
+                if (hc == MLP_HC) {
+                    mlp_gelu_split32(r1, bias + 32, oscale, hi, lo);
+                    tmem_st_32x16(hi_addr + 16u, hi);
+                    tmem_st_32x16(lo_addr + 16u, lo);
                 }
-                mbar_wait(&h_empty[b], (use & 1u) ^ 1u);              // G2 of chunk g - 2 has read h[b]
-                tcgen05_fence_after();
-                const uint32_t h_addr = tmem_base + lane_sel + (uint32_t)MLP_TM_H + b * 64u + (uint32_t)half * 16u;
-                tmem_st_32x16(h_addr, hi);
-                tmem_st_32x16(h_addr + 32u, lo);
                 tmem_st_wait_all();
                 tcgen05_fence_before();
                 __syncwarp();
@@ -1178,11 +1208,17 @@ int launch_mlp(const MlpArgs& g, cudaStream_t st) {
     MlpParams mp;
     mp.M = g.M;
     mp.C = C;
-    mp.nch = hidden / MLP_HC;
+    mp.hidden = hidden;
+    mp.nch = (hidden + MLP_HC - 1) / MLP_HC;
     mp.m_tiles = (int)((g.M + 2 * BM - 1) / (2 * BM));
     mp.kb = (C + BKW - 1) / BKW;
     mp.out_scale = g.out_scale;
     mp.bias1 = g.b1;
+    static const int stagger = [] {
+        const char* e = getenv("PAFUSE_MLP_STAGGER");
+        return e ? atoi(e) : 8000;
+    }();
+    mp.stagger = mp.m_tiles >= 4 * (g_num_sms / 2) ? stagger : 0;     // only worth it for launches many tiles long
     mp.ep = KernelParams();
     mp.ep.M = g.M;
     mp.ep.N = C;
@@ -1203,7 +1239,11 @@ int launch_mlp(const MlpArgs& g, cudaStream_t st) {
     const int fixed = 1024 + mp.kb * 2 * MLP_A_BOX_BYTES + STG_BYTES;
     int stages = (max_dyn - fixed) / MLP_STAGE_BYTES;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages < 3) {
+    if (const char* e = getenv("PAFUSE_MLP_STAGES")) {                // experiment: fewer stages than fit
+        const int cap = atoi(e);
+        if (cap >= 2 && cap < stages) stages = cap;
+    }
+    if (stages < 2) {
         set_last_error("mlp_fused: C=%d leaves room for %d weight stages only", C, stages);
         return -1;
     }
@@ -1213,7 +1253,7 @@ int launch_mlp(const MlpArgs& g, cudaStream_t st) {
     CUtensorMap ah, al, w1h, w1l, w2h, w2l, ox, oh, ol;
     if (int rc = make_map_f16(&ah, g.a_hi, g.M, C, BM)) return rc;
     if (int rc = make_map_f16(&al, g.a_lo, g.M, C, BM)) return rc;
-    if (int rc = make_map_f16(&w1h, g.w1_hi, hidden, C, MLP_HC / 2)) return rc;
+    if (int rc = make_map_f16(&w1h, g.w1_hi, hidden, C, MLP_HC / 2)) return rc;     // 64-row boxes (this CTA's half of a chunk)
     if (int rc = make_map_f16(&w1l, g.w1_lo, hidden, C, MLP_HC / 2)) return rc;
     if (int rc = make_map_f16(&w2h, g.w2_hi, C, hidden, C / 2, 32)) return rc;
     if (int rc = make_map_f16(&w2l, g.w2_lo, C, hidden, C / 2, 32)) return rc;
