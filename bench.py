@@ -273,6 +273,7 @@ def run_ours(args):
     post.profile_enable(True)
     ms_profiled = timed(step_resident, args.steps, 0)
     prof = ctx.profile_read()
+    prof_bytes = ctx.profile_read_bytes()
     prof_post = post.profile_read()
     ctx.profile_enable(False)
     post.profile_enable(False)
@@ -290,6 +291,10 @@ def run_ours(args):
                      ("tflops" if k in ("gemm", "attention") else "gbs"):
                          (v[1] / (v[0] * 1e-3) / (1e12 if k in ("gemm", "attention") else 1e9)) if v[0] > 0 else 0.0}
                  for k, v in {**prof, "post": prof_post["post"]}.items()}
+    for k in ("gemm", "attention"):                                    # the same launches seen as DRAM traffic
+        if prof[k][0] > 0:
+            breakdown[k]["gbs"] = prof_bytes[k] / (prof[k][0] * 1e-3) / 1e9
+    path_gbs = sum(prof_bytes.values()) / (ms_profiled * args.steps * 1e-3) / 1e9 if ms_profiled > 0 else 0.0
     line = {
         "metric": "whole-body 3D frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -306,6 +311,12 @@ def run_ours(args):
             "frac": gemm_tflops / tensor_peak, "traffic": gemm_traffic(),
             "flops_per_launch": g_flops / g_n if g_n else None, "ms_per_launch": g_ms / g_n if g_n else None,
             "peak_source": f"{peaks['source']} bf16_tflops_sustained",
+            "hbm_view": {"achieved": breakdown["gemm"].get("gbs"), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": breakdown["gemm"].get("gbs", 0.0) / peaks["hbm_gbs"],
+                         "path_gbs": path_gbs, "path_frac": path_gbs / peaks["hbm_gbs"],
+                         "note": "algorithmic DRAM bytes (fp16 hi/lo operands and results once, weights once, residual "
+                                 "read + write) of the same launches / the same time: the proj and fc2 launches are "
+                                 "DRAM-bound, qkv and fc1 tensor / epilogue bound (DESIGN.md section 9)"},
             "note": "achieved = algorithmic 2*M*N*K of the fp32 layer (the 3 fp16 tensor-core passes are not "
                     "counted, so the ceiling of frac is 1/3) / CUDA-event time of the GEMM launches of the "
                     "profiled repeat of the timed steps, rank 0; traffic = mean DRAM bytes per GEMM launch from the "

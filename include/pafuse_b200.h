@@ -150,6 +150,9 @@ int pafuse_keypoints_from_detections(pafuse_ctx* ctx, const float* raw, int64_t 
 #define PAFUSE_PROFILE_CATEGORIES 6
 int pafuse_profile_enable(pafuse_ctx* ctx, int32_t enable);
 int pafuse_profile_read(pafuse_ctx* ctx, double* ms, double* work, int64_t* launches, int32_t ncat);
+/* the same records seen as DRAM traffic: per category the algorithmic bytes (operands read once, results written
+ * once; for the GEMMs fp16 hi/lo operands, the weight matrix once, and the epilogue's reads and writes) */
+int pafuse_profile_read_bytes(pafuse_ctx* ctx, double* bytes, int32_t ncat);
 
 /* ---- unit-level entry points (tests and profiling; same kernels the path uses) ---- */
 

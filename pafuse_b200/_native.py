@@ -50,6 +50,7 @@ _SIGNATURES = {
     "pafuse_keypoints_from_detections": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "pafuse_profile_enable": (c_int32, [c_void_p, c_int32]),
     "pafuse_profile_read": (c_int32, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64), c_int32]),
+    "pafuse_profile_read_bytes": (c_int32, [c_void_p, POINTER(c_double), c_int32]),
     "pafuse_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                 c_int32, c_void_p]),
     "pafuse_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
@@ -318,6 +319,13 @@ class NativeContext:
         with torch.cuda.device(self.device):
             check(self.lib.pafuse_profile_read(self.handle, ms, work, cnt, n), "pafuse_profile_read")
         return {name: (ms[i], work[i], int(cnt[i])) for i, name in enumerate(self.PROFILE_CATEGORIES)}
+
+    def profile_read_bytes(self):
+        """{category: algorithmic DRAM bytes} of the launches recorded since profile_enable(True)."""
+        n = len(self.PROFILE_CATEGORIES)
+        b = (c_double * n)()
+        check(self.lib.pafuse_profile_read_bytes(self.handle, b, n), "pafuse_profile_read_bytes")
+        return {name: b[i] for i, name in enumerate(self.PROFILE_CATEGORIES)}
 
     def set_debug_simt_attention(self, enable: bool):
         check(self.lib.pafuse_set_debug_simt_attention(self.handle, 1 if enable else 0), "pafuse_set_debug_simt_attention")

@@ -78,6 +78,7 @@ enum ProfCat { CAT_GEMM = 0, CAT_ATTN, CAT_LN, CAT_EMBED_HEAD, CAT_DDIM, CAT_POS
 struct ProfRec {
     int cat;
     double work;          // algorithmic FLOPs (GEMM, attention) or bytes (the rest) of this launch
+    double bytes;         // algorithmic DRAM bytes of this launch (operands read once, results written once)
     cudaEvent_t a, b;
 };
 
@@ -136,11 +137,12 @@ struct ProfScope {
     cudaStream_t st;
     size_t idx = 0;
     bool active;
-    ProfScope(pafuse_ctx* c, int cat, double work, cudaStream_t s) : ctx(c), st(s), active(c->prof.on) {
+    ProfScope(pafuse_ctx* c, int cat, double work, cudaStream_t s, double bytes = -1.0) : ctx(c), st(s), active(c->prof.on) {
         if (!active) return;
         ProfRec r;
         r.cat = cat;
         r.work = work;
+        r.bytes = bytes >= 0.0 ? bytes : (cat == CAT_GEMM || cat == CAT_ATTN ? 0.0 : work);
         r.a = c->prof.get();
         r.b = c->prof.get();
         cudaEventRecord(r.a, st);
@@ -240,8 +242,18 @@ int ensure_pred(pafuse_ctx* ctx, size_t floats) {
     return 0;
 }
 
+// algorithmic DRAM bytes of one GEMM launch: fp16 hi/lo operands (4 B per element) read once, W once, and the
+// epilogue's traffic (planes / hidden hi+lo: 4 B; residual read + write: 8 B; + LayerNorm output hi+lo: 4 B)
+double gemm_bytes(const GemmArgs& g) {
+    const double mn = (double)g.M * g.N;
+    double out = 4.0 * mn;
+    if (g.epilogue == EPI_RESID) out = 8.0 * mn;
+    if (g.epilogue == EPI_RESID_LN) out = 12.0 * mn;
+    return 4.0 * (double)g.M * g.K + 4.0 * (double)g.N * g.K + out;
+}
+
 int run_gemm(pafuse_ctx* ctx, const GemmArgs& g, cudaStream_t st) {
-    ProfScope ps(ctx, CAT_GEMM, 2.0 * (double)g.M * g.N * g.K, st);
+    ProfScope ps(ctx, CAT_GEMM, 2.0 * (double)g.M * g.N * g.K, st, gemm_bytes(g));
     return ctx->debug_simt ? launch_gemm_simt(g, st) : launch_gemm_tcgen05(g, st);
 }
 
@@ -326,10 +338,10 @@ int run_part(pafuse_ctx* ctx, int pi, Workspace& w, const float* x2d, const floa
             g.out_f32 = nullptr; g.out_hi = g.out_lo = nullptr;
             g.N = 24 * pl.hds; g.epilogue = EPI_PLANES; g.planes = pl;
             {
-                ProfScope ps(ctx, CAT_GEMM, 2.0 * (double)M * 3 * C * C, st);   // algorithmic N = 3C (pad columns not counted)
+                ProfScope ps(ctx, CAT_GEMM, 2.0 * (double)M * 3 * C * C, st, gemm_bytes(g));   // algorithmic N = 3C (pad columns not counted)
                 if (int rc = ctx->debug_simt ? launch_gemm_simt(g, st) : launch_gemm_tcgen05(g, st)) return rc;
             }
-            ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st);
+            ProfScope ps(ctx, CAT_ATTN, 4.0 * (double)M * L * C, st, 4.0 * 24.0 * (double)M * pl.hds + 4.0 * (double)M * C);
             if (int rc = launch_attention_tc(pl, w.o_hi, w.o_lo, Sc, F, J, C, temporal ? 1 : 0, st, sm_limit)) return rc;
         }
 
@@ -371,7 +383,7 @@ int run_part(pafuse_ctx* ctx, int pi, Workspace& w, const float* x2d, const floa
             if (blk == 0) m.ln.add_f = p.w("Temporal_pos_embed");
             m.ln.g1 = p.w(bn + "norm1.weight"); m.ln.b1 = p.w(bn + "norm1.bias"); m.ln.eps1 = 1e-6f;
             m.ln.J = J; m.ln.F = F;
-            ProfScope ps(ctx, CAT_GEMM, 2.0 * 2.0 * (double)M * C * 2 * C, st);
+            ProfScope ps(ctx, CAT_GEMM, 2.0 * 2.0 * (double)M * C * 2 * C, st, 16.0 * (double)M * C + 16.0 * (double)C * C);
             if (int rc = launch_mlp_fused(m, st)) return rc;
             continue;
         }
@@ -925,6 +937,17 @@ int pafuse_profile_read(pafuse_ctx* ctx, double* ms, double* work, int64_t* laun
         work[r.cat] += r.work;
         launches[r.cat] += 1;
     }
+    return 0;
+}
+
+int pafuse_profile_read_bytes(pafuse_ctx* ctx, double* bytes, int32_t ncat) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!bytes || ncat < CAT_COUNT) {
+        set_last_error("pafuse_profile_read_bytes: need room for %d categories", (int)CAT_COUNT);
+        return PAFUSE_E_ARG;
+    }
+    for (int i = 0; i < ncat; ++i) bytes[i] = 0.0;
+    for (ProfRec& r : ctx->prof.recs) bytes[r.cat] += r.bytes;
     return 0;
 }
 
