@@ -707,7 +707,6 @@ struct MlpParams {
     int m_tiles;                     // tiles of 256 rows
     int stages;                      // weight ring depth
     int kb;                          // 64-wide K boxes of the A tile = ceil(C / 64)
-    int stagger;                     // start delay, in cycles, per step of (CTA pair % 4)
     float out_scale;
     const float* bias1;              // [2C]
     KernelParams ep;                 // the EPI_RESID_LN epilogue's view: N = C, bias = b2, ln
@@ -821,15 +820,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 }
             };
             const uint32_t w2_bytes = (uint32_t)(2 * w2_rows * 64);
-            // Every tile costs the same, so CTA pairs started together stay in lock-step: all of them run the
-            // DRAM-heavy LayerNorm epilogue (12 bytes per element) at the same time, DRAM saturates for that phase
-            // and idles during the chunk phases.  A one-time start offset per pair spreads the epilogues over the
-            // tile period.
-            if (p.stagger > 0 && (pair & 3) != 0) {
-                const long long t0 = clock64(), wait_for = (long long)(pair & 3) * p.stagger;
-                while (clock64() - t0 < wait_for) {
-                }
-            }
+            // (Start offsets per CTA pair, to keep the pairs from running their DRAM-heavy epilogues in lock-step, and
+            // weight rings of 2 / 3 / 4 stages all measured the same: profiles/r1n_mlp_fused.txt.)
             for (int i = 0; i < n_local; ++i) {
                 const int tile = pair + i * num_pairs;
                 const int m0 = (tile * CG + (int)cta_rank) * BM;
@@ -1214,11 +1206,6 @@ int launch_mlp(const MlpArgs& g, cudaStream_t st) {
     mp.kb = (C + BKW - 1) / BKW;
     mp.out_scale = g.out_scale;
     mp.bias1 = g.b1;
-    static const int stagger = [] {
-        const char* e = getenv("PAFUSE_MLP_STAGGER");
-        return e ? atoi(e) : 8000;
-    }();
-    mp.stagger = mp.m_tiles >= 4 * (g_num_sms / 2) ? stagger : 0;     // only worth it for launches many tiles long
     mp.ep = KernelParams();
     mp.ep.M = g.M;
     mp.ep.N = C;
@@ -1239,10 +1226,6 @@ int launch_mlp(const MlpArgs& g, cudaStream_t st) {
     const int fixed = 1024 + mp.kb * 2 * MLP_A_BOX_BYTES + STG_BYTES;
     int stages = (max_dyn - fixed) / MLP_STAGE_BYTES;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (const char* e = getenv("PAFUSE_MLP_STAGES")) {                // experiment: fewer stages than fit
-        const int cap = atoi(e);
-        if (cap >= 2 && cap < stages) stages = cap;
-    }
     if (stages < 2) {
         set_last_error("mlp_fused: C=%d leaves room for %d weight stages only", C, stages);
         return -1;
