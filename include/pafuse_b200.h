@@ -172,6 +172,14 @@ int pafuse_attention(pafuse_ctx* ctx, const float* qkv, float* out, int32_t S, i
 int pafuse_qkv_attention(pafuse_ctx* ctx, const float* x, const float* w, const float* b, float* out, int32_t S,
                          int32_t J, int32_t C, int32_t temporal, void* stream);
 
+/* Mlp.forward of a block with what follows it (mixste.py:37-43, :115, and the norms of :243-273), the way the path
+ * runs it for the parts with C <= 256:  x <- x + fc2(GELU(fc1(a)));  g0 != NULL: x <- LN(x; g0, bb0);
+ * a_out = LN(x; g1, bb1) (as the fp32 sum of its fp16 hi/lo pair).  fused != 0: one launch (mlp_fused_kernel),
+ * else the fc1 and fc2 GEMM launches.  a [M,C], w1 [2C,C], b1 [2C], w2 [C,2C], b2 [C], x [M,C] in/out. */
+int pafuse_mlp_block(pafuse_ctx* ctx, const float* a, const float* w1, const float* b1, const float* w2, const float* b2,
+                     float* x, const float* g0, const float* bb0, const float* g1, const float* bb1, float* a_out, int64_t M,
+                     int32_t C, int32_t fused, void* stream);
+
 /* debugging switch: route the path's GEMMs through the CUDA-core reference kernel */
 int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable);
 /* debugging switch: CUDA-core attention kernel instead of the tcgen05 one */

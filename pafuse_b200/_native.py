@@ -59,6 +59,7 @@ _SIGNATURES = {
     "pafuse_set_debug_simt_gemm": (c_int32, [c_void_p, c_int32]),
     "pafuse_set_gemm_cta_group": (c_int32, [c_int32]),
     "pafuse_set_gemm_weight_stationary": (c_int32, [c_int32]),
+    "pafuse_mlp_block": (c_int32, [c_void_p] * 12 + [c_int64, c_int32, c_int32, c_void_p]),
     "pafuse_set_fuse_layernorm": (c_int32, [c_void_p, c_int32]),
     "pafuse_set_part_streams": (c_int32, [c_void_p, c_int32, c_void_p]),
     "pafuse_set_fuse_mlp": (c_int32, [c_void_p, c_int32]),
@@ -259,6 +260,21 @@ class NativeContext:
             check(self.lib.pafuse_qkv_attention(self.handle, _ptr(x), _ptr(w), _ptr(b), _ptr(out), S, J, C,
                                                 1 if temporal else 0, _stream()), "pafuse_qkv_attention")
         return out
+
+    def mlp_block(self, a, w1, b1, w2, b2, x, g1, bb1, g0=None, bb0=None, fused=True):
+        """(x', a_out): x' = x + fc2(GELU(fc1(a))) [then LN(.; g0, bb0)], a_out = LN(x'; g1, bb1); see pafuse_mlp_block."""
+        a, w1, b1, w2, b2 = (_f32c(t, self.device) for t in (a, w1, b1, w2, b2))
+        g1, bb1 = _f32c(g1, self.device), _f32c(bb1, self.device)
+        g0 = None if g0 is None else _f32c(g0, self.device)
+        bb0 = None if bb0 is None else _f32c(bb0, self.device)
+        x = _f32c(x, self.device).clone()
+        M, C = a.shape
+        a_out = torch.empty_like(a)
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_mlp_block(self.handle, _ptr(a), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(x), _ptr(g0),
+                                            _ptr(bb0), _ptr(g1), _ptr(bb1), _ptr(a_out), M, C, 1 if fused else 0, _stream()),
+                  "pafuse_mlp_block")
+        return x, a_out
 
     def set_debug_simt_gemm(self, enable: bool):
         check(self.lib.pafuse_set_debug_simt_gemm(self.handle, 1 if enable else 0), "pafuse_set_debug_simt_gemm")

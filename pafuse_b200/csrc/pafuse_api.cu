@@ -1075,4 +1075,53 @@ int pafuse_qkv_attention(pafuse_ctx* ctx, const float* x, const float* w, const 
     return rc;
 }
 
+int pafuse_mlp_block(pafuse_ctx* ctx, const float* a, const float* w1, const float* b1, const float* w2, const float* b2,
+                     float* x, const float* g0, const float* bb0, const float* g1, const float* bb1, float* a_out, int64_t M,
+                     int32_t C, int32_t fused, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (!a || !w1 || !b1 || !w2 || !b2 || !x || !g1 || !bb1 || !a_out || (g0 && !bb0) || M < 1 || !mlp_can_fuse(C)) {
+        set_last_error("pafuse_mlp_block: bad argument (C %% 32 == 0, 64 <= C <= 256)");
+        return PAFUSE_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)M * C, nw = (size_t)2 * C * C;
+    op_t *ah = nullptr, *al = nullptr, *w1h = nullptr, *w1l = nullptr, *w2h = nullptr, *w2l = nullptr, *hh = nullptr,
+         *hl = nullptr, *oh = nullptr, *ol = nullptr;
+    int rc = 0;
+    if (dev_alloc(&ah, n) || dev_alloc(&al, n) || dev_alloc(&w1h, nw) || dev_alloc(&w1l, nw) || dev_alloc(&w2h, nw) ||
+        dev_alloc(&w2l, nw) || dev_alloc(&oh, n) || dev_alloc(&ol, n) || (!fused && (dev_alloc(&hh, 2 * n) || dev_alloc(&hl, 2 * n))))
+        rc = PAFUSE_E_CUDA;
+    if (!rc) {
+        split_rows_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w1, w1h, w1l, nw, WEIGHT_SCALE);   // weights first, see pafuse_linear
+        split_rows_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w2, w2h, w2l, nw, WEIGHT_SCALE);
+        split_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, ah, al, n, 1.0f);
+        GemmLnFuse ln;
+        ln.x = x; ln.g0 = g0; ln.b0 = bb0; ln.g1 = g1; ln.b1 = bb1; ln.eps0 = 1e-6f; ln.eps1 = 1e-6f;
+        if (fused) {
+            MlpArgs m;
+            m.a_hi = ah; m.a_lo = al; m.w1_hi = w1h; m.w1_lo = w1l; m.b1 = b1; m.w2_hi = w2h; m.w2_lo = w2l; m.b2 = b2;
+            m.x = x; m.out_hi = oh; m.out_lo = ol; m.M = M; m.C = C; m.ln = ln;
+            rc = launch_mlp_fused(m, st);
+        } else {
+            GemmArgs g;
+            g.a_hi = ah; g.a_lo = al; g.w_hi = w1h; g.w_lo = w1l; g.bias = b1; g.out_f32 = nullptr; g.out_hi = hh; g.out_lo = hl;
+            g.M = M; g.N = 2 * C; g.K = C; g.epilogue = EPI_GELU_SPLIT;
+            rc = launch_gemm_tcgen05(g, st);
+            g = GemmArgs();
+            g.a_hi = hh; g.a_lo = hl; g.w_hi = w2h; g.w_lo = w2l; g.bias = b2; g.out_f32 = x; g.out_hi = oh; g.out_lo = ol;
+            g.M = M; g.N = C; g.K = 2 * C; g.epilogue = EPI_RESID_LN; g.ln = ln;
+            if (!rc) rc = launch_gemm_tcgen05(g, st);
+        }
+        if (!rc) join_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(oh, ol, a_out, n);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(ah); cudaFree(al); cudaFree(w1h); cudaFree(w1l); cudaFree(w2h); cudaFree(w2l); cudaFree(hh); cudaFree(hl);
+    cudaFree(oh); cudaFree(ol);
+    if (!rc && e != cudaSuccess) {
+        set_last_error("pafuse_mlp_block: %s", cudaGetErrorString(e));
+        rc = PAFUSE_E_CUDA;
+    }
+    return rc;
+}
+
 }  // extern "C"

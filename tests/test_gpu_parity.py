@@ -79,6 +79,36 @@ def test_linear_ragged_rows(M):
     assert (out.double() - ref).abs().max().item() < 5e-5
 
 
+@pytest.mark.parametrize("C", [64, 128, 224, 256])
+@pytest.mark.parametrize("M", [1, 255, 256, 257, 74 * 256 + 513])
+@pytest.mark.parametrize("chained", [False, True])
+def test_mlp_block_one_kernel_against_two_launches_and_fp64(C, M, chained):
+    """pafuse_mlp_block: x + fc2(GELU(fc1(a))) and the LayerNorms that follow, as ONE kernel (hidden activations in
+    tensor memory) against the fc1 / fc2 GEMM launches (same MMAs in the same order) and against fp64 torch; ragged
+    row counts, a tile per CTA pair and several, hidden widths with and without a 64-column last chunk."""
+    import torch.nn.functional as Fn
+    torch.manual_seed(C + M)
+    c = _ctx()
+    dev = "cuda"
+    a = torch.randn(M, C, device=dev)
+    x = torch.randn(M, C, device=dev)
+    w1 = (torch.rand(2 * C, C, device=dev) * 2 - 1) / C ** 0.5
+    w2 = (torch.rand(C, 2 * C, device=dev) * 2 - 1) / (2 * C) ** 0.5
+    b1, b2 = torch.randn(2 * C, device=dev) * 0.1, torch.randn(C, device=dev) * 0.1
+    g1, bb1 = 1 + 0.1 * torch.randn(C, device=dev), 0.1 * torch.randn(C, device=dev)
+    g0, bb0 = (1 + 0.1 * torch.randn(C, device=dev), 0.1 * torch.randn(C, device=dev)) if chained else (None, None)
+    xf, af = c.mlp_block(a, w1, b1, w2, b2, x, g1, bb1, g0, bb0, fused=True)
+    xs, as_ = c.mlp_block(a, w1, b1, w2, b2, x, g1, bb1, g0, bb0, fused=False)
+    assert (xf - xs).abs().max().item() < 1e-5 and (af - as_).abs().max().item() < 1e-5
+    d = lambda t: t.double()
+    v = d(x) + Fn.linear(Fn.gelu(Fn.linear(d(a), d(w1), d(b1))), d(w2), d(b2))
+    if chained:
+        v = Fn.layer_norm(v, (C,), d(g0), d(bb0), 1e-6)
+    ref_a = Fn.layer_norm(v, (C,), d(g1), d(bb1), 1e-6)
+    assert (d(xf) - v).abs().max().item() < 3e-5
+    assert (d(af) - ref_a).abs().max().item() < 3e-5
+
+
 @pytest.mark.parametrize("N,K", [(1152, 384), (384, 384), (768, 384), (768, 224), (224, 224), (448, 224), (768, 256),
                                  (256, 256), (512, 256), (32, 64)])
 @pytest.mark.parametrize("epi", [0, 1, 2])
