@@ -20,6 +20,10 @@ def lin(x, w, b):
         return xh @ wh.t() + (xl.half().float() @ wh.t()) + (xh @ wl.half().float().t()) + b
     if MODE == 'f16x1':
         return xh @ wh.t() + b
+    if MODE == 'lo8':
+        # activations stored as fp16 hi + e4m3 lo: A_hi W_hi and A_hi W_lo in fp16, A_lo W_hi in FP8 (e4m3 weight copy)
+        sxl, swh = pow2scale(xl), pow2scale(wh)
+        return xh @ wh.t() + xh @ wl.half().float().t() + f8(xl, sxl) @ f8(wh, swh).t() + b
     # fp8 corrections
     sxl, swh, sxh, swl = pow2scale(xl), pow2scale(wh), pow2scale(xh), pow2scale(wl)
     c1 = f8(xl, sxl) @ f8(wh, swh).t()
@@ -54,7 +58,7 @@ def run(mode):
     return orc.ddim_sample_flip(sd, parts, x2d, x2df, noises, sk.joints_left, sk.joints_right, H, K, depth=depth)
 with torch.no_grad():
     ref = run('exact')
-    for m in ['f16x3', 'fp8corr', 'f16x1']:
+    for m in ['f16x3', 'lo8', 'fp8corr', 'f16x1']:
         out = run(m)
         d = out - ref
         viol = (d.abs() > 1e-3 * ref.abs() + 2e-5).float().mean().item()
