@@ -182,7 +182,8 @@ def workload_config(args):
                         f"num_proposals={args.proposals}, sampling_timesteps={args.timesteps}, flip-TTA, depth 8, "
                         "lift = D3DP.forward + wb_pose_from_parts + J-Agg/P-Agg",
             "clips_per_gpu": args.clips, "num_proposals": args.proposals, "sampling_timesteps": args.timesteps,
-            "parallelism": f"clip-sharded x{args.gpus}", "l2": "L2 flushed (512 MiB write) before every timed step"}
+            "parallelism": f"{'clip' if getattr(args, 'shard', 'clips') == 'clips' else 'hypothesis'}-sharded x{args.gpus}",
+            "l2": "L2 flushed (512 MiB write) before every timed step"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -206,7 +207,7 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     H, K, Bl = args.proposals, args.timesteps, args.clips
-    B = Bl * world
+    B = Bl * world if args.shard == "clips" else Bl
     sk = H3WBSkeleton()
     model = pafuse_b200.D3DP(synthetic.default_args(depth=8), sk.joints_left, sk.joints_right, sk, is_train=False,
                              num_proposals=H, sampling_timesteps=K)
@@ -224,11 +225,11 @@ def run_ours(args):
     ctx, post = model.native_context(dev), utils._post_context(dev)
 
     def step_resident(seed):
-        return pd.lift_sharded(engine, x2d, x2df, traj, cam, H, mode="clips", seed=seed, rank=rank, world=world)
+        return pd.lift_sharded(engine, x2d, x2df, traj, cam, H, mode=args.shard, seed=seed, rank=rank, world=world)
 
     def step_e2e(seed):
         a, b, t = x2d_h.to(dev, non_blocking=True), x2df_h.to(dev, non_blocking=True), traj_h.to(dev, non_blocking=True)
-        res = pd.lift_sharded(engine, a, b, t, cam, H, mode="clips", seed=seed, rank=rank, world=world)
+        res = pd.lift_sharded(engine, a, b, t, cam, H, mode=args.shard, seed=seed, rank=rank, world=world)
         out_h[0].copy_(res.jagg, non_blocking=True)
         out_h[1].copy_(res.pagg, non_blocking=True)
         return res
@@ -297,7 +298,7 @@ def run_ours(args):
     path_gbs = sum(prof_bytes.values()) / (ms_profiled * args.steps * 1e-3) / 1e9 if ms_profiled > 0 else 0.0
     line = {
         "metric": "whole-body 3D frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak" if args.shard == "clips" else "strong", "vs_baseline": None,
         "dtype": "f16x3 (fp32 operands carried as fp16 hi/lo pairs, 3 tcgen05 passes, fp32 accumulate)", "data": "synthetic",
         "config": workload_config(args),
         "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
@@ -353,6 +354,10 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=1, help="clips in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-seqs", type=int, default=0, help="sequences per workspace pass (0 = library default)")
+    ap.add_argument("--shard", default="clips", choices=["clips", "hypotheses"],
+                    help="clips: every GPU lifts its own --clips clips (weak scaling, the default and the driver's run); "
+                         "hypotheses: the same --clips clips on every GPU, --proposals split across the GPUs "
+                         "(BASELINE configs[2], strong scaling, one all-to-all before the aggregation)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
