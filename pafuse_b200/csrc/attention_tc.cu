@@ -143,8 +143,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     constexpr uint32_t LAYOUT = HDP == 64 ? 2u : 4u;
     constexpr uint32_t SBO = 8 * ROWB;
     constexpr int NCH_MAX = LT ? (LT + 31) / 32 : 4;           // 32-column score chunks of one group
+    // operand ring slots: unit `it` loads into slot it % NS.  Two tensor-memory stages bound the units in flight, but
+    // the 48 KB stages of the narrow heads leave room for four slots, so Q, K, V are requested three units ahead
+    // instead of one and their DRAM latency no longer sits inside the unit's QK -> softmax -> PV chain.
+    constexpr int NS = HDP == 32 ? 4 : 2;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t qk_full[2], qk_empty[2], v_full[2], v_empty[2];
+    __shared__ __align__(8) uint64_t qk_full[NS], qk_empty[NS], v_full[NS], v_empty[NS];
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2], p_full[2], o_full[2], o_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
@@ -168,18 +172,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
     pdl_launch_dependents();
     // rows no box ever writes must not hold NaN bit patterns (0 * NaN in the PV product)
-    for (int i = threadIdx.x; i < 2 * STAGE_BYTES / 16; i += ATT_THREADS)
+    for (int i = threadIdx.x; i < NS * STAGE_BYTES / 16; i += ATT_THREADS)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
 
     if (warp == 1 && lane == 0) {
         prefetch_tensormap(&tm_hi);
         prefetch_tensormap(&tm_lo);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&qk_full[s], 1);
             mbar_init(&qk_empty[s], 1);
             mbar_init(&v_full[s], 1);
             mbar_init(&v_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], n_live);
             mbar_init(&p_full[s], n_live);                     // one lane per live warp of the stage's softmax group
@@ -206,10 +212,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         if (lane == 0) {
             const int stage = warp == 0 ? 0 : 1;
             const uint32_t tile_tx = (uint32_t)(rows_box * ROWB);          // zero-filled rows count too
-            uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
             for (int it = stage; it < n_local; it += 2) {
                 const int u = (int)blockIdx.x + it * (int)gridDim.x;
-                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                const int slot = it % NS;
+                const uint32_t ph = (uint32_t)(it / NS) & 1u;
+                uint8_t* st = smem + (size_t)slot * STAGE_BYTES;
                 const int tile = u >> 3, head = u & 7;
                 int ca, cb;                                    // spatial: (first sequence, -) ; temporal: (j0, s)
                 if (!p.temporal) {
@@ -223,13 +230,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 for (int w = 0; w < 3; ++w) {                  // q, k, v
                     const int plane = w * 8 + head;
                     if (w == 0) {
-                        mbar_wait(&qk_empty[stage], ph ^ 1);   // QK^T of the unit that last used this stage has retired
-                        mbar_arrive_expect_tx(&qk_full[stage], 4 * tile_tx);
+                        mbar_wait(&qk_empty[slot], ph ^ 1);    // QK^T of the unit that last used this slot has retired
+                        mbar_arrive_expect_tx(&qk_full[slot], 4 * tile_tx);
                     } else if (w == 2) {
-                        mbar_wait(&v_empty[stage], ph ^ 1);    // PV of that unit has retired
-                        mbar_arrive_expect_tx(&v_full[stage], 2 * tile_tx);
+                        mbar_wait(&v_empty[slot], ph ^ 1);     // PV of that unit has retired
+                        mbar_arrive_expect_tx(&v_full[slot], 2 * tile_tx);
                     }
-                    uint64_t* bar = w == 2 ? &v_full[stage] : &qk_full[stage];
+                    uint64_t* bar = w == 2 ? &v_full[slot] : &qk_full[slot];
                     if (!p.temporal) {
                         tma_load_4d(st + (2 * w) * TILE_BYTES, &tm_hi, bar, 0, 0, ca, plane);
                         tma_load_4d(st + (2 * w + 1) * TILE_BYTES, &tm_lo, bar, 0, 0, ca, plane);
@@ -248,7 +255,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             const int stage = warp - 1;
             const uint32_t idesc_qk = make_idesc_f16(128, (uint32_t)(key_steps * 16));
             const uint32_t idesc_pv = make_idesc_f16(128, HDP) | (1u << 16);      // B (= V) is MN-major
-            const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+            const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);   // slot of this issuer's first unit
             const uint32_t d_s = tmem_base + (uint32_t)(p.tm_s0 + stage * p.tm_stride_s);
             const uint32_t d_o = tmem_base + (uint32_t)(p.tm_o0 + stage * p.tm_stride_o);
             // n_acc = 3: the passes go to accumulators 0, 1, 2; n_acc = 2: lo*hi and hi*hi -> 0, hi*lo -> 1; n_acc = 1: all -> 0
@@ -262,9 +269,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             const uint64_t kh0 = make_desc(sa + 2 * TILE_BYTES, SBO, LAYOUT), kl0 = make_desc(sa + 3 * TILE_BYTES, SBO, LAYOUT);
             const uint64_t vh0 = make_desc(sa + 4 * TILE_BYTES, SBO, LAYOUT), vl0 = make_desc(sa + 5 * TILE_BYTES, SBO, LAYOUT);
             constexpr uint64_t V_STEP = (16u * ROWB) >> 4;
+            // this issuer's units it = stage, stage + 2, ... sit in slots stage, stage + 2 (mod NS): descriptor offset of a slot
+            auto slot_off = [&](int it) { return (uint64_t)(((it % NS) - stage) * (STAGE_BYTES >> 4)); };
             auto issue_qk = [&](int it) {
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(&qk_full[stage], ph);
+                const int slot = it % NS;
+                const uint64_t so = slot_off(it);
+                mbar_wait(&qk_full[slot], (uint32_t)(it / NS) & 1u);
                 if (SEP) mbar_wait(&s_empty[stage], ph ^ 1);   // the softmax group has read S of unit it-2
                 tcgen05_fence_after();
                 // aliased layout: S[stage] overwrites P[stage] of unit it-2; that PV was issued by this thread
@@ -272,22 +283,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < HDP / 16; ++k) {
                     const uint64_t ko = (uint64_t)(k * 2);     // 32 bytes along the row, in 16-byte descriptor units
-                    umma_f16_ss<1>(d_s, ql0 + ko, kh0 + ko, idesc_qk, k != 0 ? 1u : 0u);
-                    umma_f16_ss<1>(d_s, qh0 + ko, kl0 + ko, idesc_qk, 1u);
-                    umma_f16_ss<1>(d_s, qh0 + ko, kh0 + ko, idesc_qk, 1u);
+                    umma_f16_ss<1>(d_s, ql0 + so + ko, kh0 + so + ko, idesc_qk, k != 0 ? 1u : 0u);
+                    umma_f16_ss<1>(d_s, qh0 + so + ko, kl0 + so + ko, idesc_qk, 1u);
+                    umma_f16_ss<1>(d_s, qh0 + so + ko, kh0 + so + ko, idesc_qk, 1u);
                 }
-                umma_commit<1>(&qk_empty[stage]);              // Q,K tiles of this stage may be overwritten
+                umma_commit<1>(&qk_empty[slot]);               // Q,K tiles of this slot may be overwritten
                 umma_commit<1>(&s_full[stage]);
             };
             if (stage < n_local) issue_qk(stage);
             for (int it = stage; it < n_local; it += 2) {
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 if (SEP && it + 2 < n_local) issue_qk(it + 2);
-                mbar_wait(&v_full[stage], ph);
+                const int slot = it % NS;
+                mbar_wait(&v_full[slot], (uint32_t)(it / NS) & 1u);
                 mbar_wait(&o_empty[stage], ph ^ 1);            // the softmax group has read O of unit it-2
                 mbar_wait(&p_full[stage], ph);                 // P of this unit is in tensor memory
                 tcgen05_fence_after();
-                uint64_t vh = vh0, vl = vl0;
+                uint64_t vh = vh0 + slot_off(it), vl = vl0 + slot_off(it);
                 uint32_t ph_a = d_phi, pl_a = d_plo;
                 for (int k = 0; k < key_steps; ++k, vh += V_STEP, vl += V_STEP, ph_a += 8u, pl_a += 8u) {
                     // 16 keys further down the V tile / 16 fp16 keys = 8 tensor-memory columns further in P
@@ -299,7 +311,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     umma_f16_ts(d_o1, ph_a, vl, idesc_pv, p.n_acc >= 2 ? first : 1u);
                     umma_f16_ts(d_o2, ph_a, vh, idesc_pv, p.n_acc >= 3 ? first : 1u);
                 }
-                umma_commit<1>(&v_empty[stage]);
+                umma_commit<1>(&v_empty[slot]);
                 umma_commit<1>(&o_full[stage]);
                 if (!SEP && it + 2 < n_local) issue_qk(it + 2);
             }
@@ -321,7 +333,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         const uint32_t phi_addr = s_addr + (uint32_t)p.tm_phi_off, plo_addr = s_addr + (uint32_t)p.tm_plo_off;
         const uint32_t o_addr = tmem_base + lane_sel + (uint32_t)(p.tm_o0 + wg * p.tm_stride_o);
         const float sc = p.scale_log2e;
-        uint8_t* stg = smem + 2 * STAGE_BYTES + (warp - 4) * p.stg_warp_bytes;   // this warp's output staging rows
+        uint8_t* stg = smem + NS * STAGE_BYTES + (warp - 4) * p.stg_warp_bytes;  // this warp's output staging rows
         uint8_t* my_row = stg + lane * p.stg_pitch;
         const int n_zero_chunks = (key_steps + 1) / 2;         // 32-key chunks the PV product reads
         const int cp_row = lane / p.chunks_per_row;            // copy-out role of this lane
@@ -574,7 +586,8 @@ int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int h
 
 template <int HDP, int LT, bool SEP>
 int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, cudaStream_t st, int sms) {
-    const int SMEM = 2 * 6 * TILE_ROWS * HDP * 2 + 8 * p.stg_warp_bytes + 1024;
+    constexpr int NS = HDP == 32 ? 4 : 2;                              // operand ring slots (see the kernel)
+    const int SMEM = NS * 6 * TILE_ROWS * HDP * 2 + 8 * p.stg_warp_bytes + 1024;
     if (SMEM > 227 * 1024) {
         set_last_error("attention_tc: head_dim %d needs %d bytes of shared memory", p.hd, SMEM);
         return -1;
