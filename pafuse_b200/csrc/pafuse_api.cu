@@ -489,7 +489,7 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
             off += p.C;
         }
     }
-    int max_seqs = cfg.max_seqs > 0 ? cfg.max_seqs : 256;
+    int max_seqs = cfg.max_seqs > 0 ? cfg.max_seqs : 640;
     int chunk = S_total < max_seqs ? S_total : max_seqs;
     // side by side needs the production kernels (the persistent ones can be sized to a share) and no per-launch
     // timing (bench.py's profiled pass measures every kernel alone on the whole GPU)

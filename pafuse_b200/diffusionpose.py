@@ -110,7 +110,7 @@ class D3DP(nn.Module):
         })
 
         self.noise_source = None          # optional callable(k, shape, device) -> tensor
-        self.max_seqs = int(getattr(getattr(args, "b200", None), "max_seqs", 0) or 256)
+        self.max_seqs = int(getattr(getattr(args, "b200", None), "max_seqs", 0) or 640)
         self._natives = {}
         self._native_dirty = True
         self._sinus_cache = {}

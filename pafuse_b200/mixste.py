@@ -89,7 +89,7 @@ class MixSTE2(nn.Module):
         self.head = nn.Sequential(nn.LayerNorm(C), nn.Linear(C, 3))
         self._natives = {}
         self._native_dirty = True
-        self.max_seqs = 256
+        self.max_seqs = 640
 
     # -- weight tracking: any (re)load or device move invalidates the packed copies
     def load_state_dict(self, *a, **k):
