@@ -184,6 +184,56 @@ def test_sampler_matches_reference_golden(name):
     _check_pose(out, c["golden"]["out"])
 
 
+def _compare_bench_shape(out, c):
+    """Sampler output against a bench-shape fixture (tests/golden/make_golden_bench_shapes.py): every step in full
+    ("out"), or the last step in full + three frames of every earlier step ("out_last" / "out_frames")."""
+    g = c["golden"]
+    if "out" in g:
+        return _check_pose(out, g["out"])
+    keep = [int(v) for v in c["g"]["keep_frames"]]
+    _check_pose(out[:, :-1][:, :, :, keep], g["out_frames"])
+    return _check_pose(out[:, -1], g["out_last"])
+
+
+def test_sampler_at_the_benchmarked_shape_H5_K5():
+    """BASELINE.json configs[1] (the bench.py headline): num_proposals=5, sampling_timesteps=5, depth 8, flip-TTA,
+    against the reference's own output for the same clip and the same injected noise (diffusionpose.py:272-316)."""
+    from pafuse_testlib import build_case
+    c = build_case("cfg2_B1_H5_K5")
+    m = _model(c)
+    out = m(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
+    assert out.shape == (1, 5, 5, 27, 134, 3)
+    _compare_bench_shape(out, c)
+
+
+def test_sampler_at_the_hypothesis_sharded_shape_H20_K10():
+    """BASELINE.json configs[2]: num_proposals=20, sampling_timesteps=10 (ten chained DDIM updates)."""
+    from pafuse_testlib import build_case
+    c = build_case("cfg3_B1_H20_K10")
+    m = _model(c)
+    out = m(c["x2d"].cuda(), None, input_2d_flip=c["x2df"].cuda())
+    assert out.shape == (1, 10, 20, 27, 134, 3)
+    _compare_bench_shape(out, c)
+
+
+def test_bench_shape_clip_inside_a_64_clip_batch():
+    """The clip of the H=5, K=5 fixture lifted as clip 0 of the 64-clip bench batch (the other 63 clips get other
+    inputs and noise): rows are independent, so its result must still match the reference's single-clip output."""
+    from pafuse_b200 import synthetic
+    from pafuse_testlib import build_case
+    c = build_case("cfg2_B1_H5_K5")
+    B = 64
+    x2d, x2df = synthetic.synthetic_inputs(B, seed=9)
+    x2d[0], x2df[0] = c["x2d"][0], c["x2df"][0]
+    noises = synthetic.synthetic_noise(B, c["H"], c["K"], seed=9)
+    for k in range(c["K"]):
+        noises[k][0] = c["noises"][k][0]
+    m = _model(c)
+    m.noise_source = lambda k, shape, device: noises[k].to(device)
+    out = m(x2d.cuda(), None, input_2d_flip=x2df.cuda())
+    _check_pose(out[:1], c["golden"]["out"])
+
+
 def test_tensor_core_gemm_equals_cuda_core_gemm_on_the_whole_model():
     from pafuse_testlib import build_case
     c = build_case("tiny_B1_H3_K2_d2")

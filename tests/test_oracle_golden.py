@@ -57,6 +57,15 @@ def test_flip_sampler_matches_reference(name, skeleton):
     assert torch.allclose(out, ref, rtol=0, atol=2e-6), (out - ref).abs().max()
 
 
+def test_flip_sampler_matches_reference_at_the_benchmarked_shape(skeleton):
+    """BASELINE.json configs[1] (H=5, K=5, depth 8), fixture of tests/golden/make_golden_bench_shapes.py.  (The
+    H=20, K=10 fixture costs minutes on the CPU: the GPU suite compares the CUDA path with it directly.)"""
+    c = build_case("cfg2_B1_H5_K5")
+    out = orc.ddim_sample_flip(c["sd"], _parts(skeleton), c["x2d"], c["x2df"], c["noises"], skeleton.joints_left,
+                               skeleton.joints_right, c["H"], c["K"], depth=c["depth"])
+    assert torch.allclose(out, c["golden"]["out"], rtol=0, atol=2e-6), (out - c["golden"]["out"]).abs().max()
+
+
 def test_noflip_sampler_matches_reference(skeleton):
     c = build_case("noflip_B2_H1_K2_d2")
     out = orc.ddim_sample_noflip(c["sd"], _parts(skeleton), c["x2d"], c["noises"], c["K"], depth=c["depth"])
