@@ -124,8 +124,11 @@ class ClockSampler:
 # CPU arm: the oracle port of the reference algorithm on the host cores (test infrastructure used
 # here only as the *baseline being reported*, never on the product path).
 # ---------------------------------------------------------------------------------------------
-def cpu_lift_sample(H, K, clips=1, threads=None, depth=8):
-    """Time one lift of `clips` clips (same H, K, flip-TTA, depth) with the oracle on the CPU."""
+def cpu_lift_sample(H, K, clips=1, threads=None, depth=8, device="cpu"):
+    """One lift of `clips` clips (same H, K, flip-TTA, depth) with the oracle: ``run()`` returns the seconds it took,
+    ``run.result`` then holds (whole-body hypotheses, jagg, pagg) and ``run.inputs`` the (x2d, x2d_flip, noises, traj)
+    it consumed.  device="cuda" runs the SAME eager fp32 torch code on the GPU (allow_tf32 off): the
+    `gpu_eager_baseline` leg, i.e. what a user of the reference's PyTorch path gets on this B200 today."""
     import torch
 
     from oracle import pafuse_oracle as orc
@@ -134,20 +137,32 @@ def cpu_lift_sample(H, K, clips=1, threads=None, depth=8):
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     sk = H3WBSkeleton()
-    sd = synthetic.synthetic_state_dict(seed=1, depth=depth)
-    x2d, x2df = synthetic.synthetic_inputs(clips, seed=1)
-    noises = synthetic.synthetic_noise(clips, H, K, seed=1)
-    traj, cam = synthetic.synthetic_trajectory(clips, seed=1), synthetic.h36m_cam0_intrinsics()
+    dev = torch.device(device)
+    sd = {k: v.to(dev) for k, v in synthetic.synthetic_state_dict(seed=1, depth=depth).items()}
+    x2d, x2df = (t.to(dev) for t in synthetic.synthetic_inputs(clips, seed=1))
+    noises = [n.to(dev) for n in synthetic.synthetic_noise(clips, H, K, seed=1)]
+    traj, cam = synthetic.synthetic_trajectory(clips, seed=1).to(dev), synthetic.h36m_cam0_intrinsics().to(dev)
     parts = merged_part_indices(sk.parts_joint_indices)
 
     def run():
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        with torch.no_grad():
+        with torch.no_grad(), torch.device(dev):
             out = orc.ddim_sample_flip(sd, parts, x2d, x2df, noises, sk.joints_left, sk.joints_right, H, K, depth=depth)
             wb, _ = orc.wb_pose_from_parts(out, sk.parts_joint_indices, sk.parts_connection_indices)
-            orc.aggregate(wb, traj, cam, x2d)
+            jagg, pagg, _ = orc.aggregate(wb, traj, cam, x2d)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        run.result = (wb, jagg, pagg)
         return time.perf_counter() - t0
+    run.inputs = (x2d, x2df, noises, traj)
+    run.result = None
     return run, threads
+
+
+CPU_SAMPLE_NOTE = ("CPU throughput of this path rises with the batch (SURVEY.md section 6: 66 -> 83 frames/s from 2 to 8 "
+                   "clips at H=K=1), so a small sample understates the CPU by perhaps 10-25 %")
 
 
 def run_reference_arm(args):
@@ -164,7 +179,8 @@ def run_reference_arm(args):
     times = [run() for _ in range(args.steps)]
     sec = sum(times) / len(times)
     fps = clips * FRAMES / sec
-    sample = f"{clips} clip(s) x {FRAMES} frames of the {args.clips}-clip batch per step, H={H} K={K} flip-TTA depth 8"
+    sample = (f"{clips} clip(s) x {FRAMES} frames of the {args.clips}-clip batch per step, H={H} K={K} flip-TTA depth 8; "
+              + CPU_SAMPLE_NOTE)
     line = {
         "impl": "reference", "metric": "whole-body 3D frames/sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
@@ -331,15 +347,135 @@ def run_ours(args):
         "kernel_breakdown": breakdown,
     }
     if world == 1 and not args.no_cpu_baseline:
-        run, threads = cpu_lift_sample(H, K, clips=args.cpu_clips)
+        # CPU baseline (oracle port, all host threads, bounded sample) -- and, with the same injected inputs and noise,
+        # the parity check of the GPU path at the benchmarked shape: the sample's clips are lifted as clips 0..n-1 of
+        # a full 64-clip batch (the other clips keep their own inputs / noise), through the same public calls.
+        n = args.cpu_clips
+        run, threads = cpu_lift_sample(H, K, clips=n)
         sec = run()
-        line["cpu_baseline"] = {"value": args.cpu_clips * FRAMES / sec, "unit": "frames/s", "cores": threads,
-                                "kind": "port", "sample": f"{args.cpu_clips} clip(s) of the {Bl}-clip batch, H={H} K={K}, "
-                                                          f"one pass ({sec:.1f} s)"}
+        line["cpu_baseline"] = {"value": n * FRAMES / sec, "unit": "frames/s", "cores": threads, "kind": "port",
+                                "sample": f"{n} clip(s) of the {Bl}-clip batch, H={H} K={K}, one pass ({sec:.1f} s); "
+                                          + CPU_SAMPLE_NOTE}
+        line["parity_check"] = parity_check(torch, pd, engine, run, (x2d, x2df, traj, cam), H, K, n, dev)
+        if not args.no_gpu_eager:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(torch, H, K, args.eager_clips, fps)
+    if world > 1:
+        line["sharding_check"] = sharding_check(torch, pd, engine, (x2d, x2df, traj, cam), H, args.shard, rank, world, dev)
+    if args.extra or (world > 1 and not args.no_extra):
+        line["extra"] = extra_configs(torch, dist, pd, model, engine, sk, timed, rank, world, dev, args)
     if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_check(torch, pd, engine, run, batch, H, K, n, dev):
+    """GPU path vs the CPU oracle on the clips the CPU sample lifted, at the benchmarked shape (reference:
+    common/diffusionpose.py:272-316 + utils.py:113-126 + the aggregation).  Tolerances are the test suite's:
+    per coordinate |d| <= 1e-3*|ref| + 2e-5 m, MPJPE delta <= 0.1 mm."""
+    x2d, x2df, traj, cam = (t.clone() for t in batch)
+    cx2d, cx2df, cnoises, ctraj = run.inputs
+    x2d[:n], x2df[:n], traj[:n] = cx2d.to(dev), cx2df.to(dev), ctraj.to(dev)
+    B = x2d.shape[0]
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    noises = []
+    for k in range(K):
+        t = torch.randn((B, H, FRAMES, 134, 3), generator=g)
+        t[:n] = cnoises[k]
+        noises.append(t.to(dev))
+    res = pd.lift(engine, x2d, x2df, traj, cam, H, noise_source=lambda k, shape, device: noises[k], keep_hypotheses=True)
+    ref_wb, ref_jagg, ref_pagg = run.result
+    d = (res.pred[:n].double().cpu() - ref_wb.double())
+    mpjpe_mm = d.norm(dim=-1).mean().item() * 1e3
+    tol_ratio = (d.abs() / (1e-3 * ref_wb.double().abs() + 2e-5)).max().item()
+    max_rel = (d.abs() / ref_wb.double().abs().clamp_min(2e-2)).max().item()
+    pagg_abs = (res.pagg[:n].double().cpu() - ref_pagg.double()).abs().max().item()
+    return {"clips": n, "shape": f"H={H} K={K} depth 8 flip-TTA, clips 0..{n - 1} of a {B}-clip batch", "mpjpe_mm": mpjpe_mm,
+            "max_rel": max_rel, "max_abs_m": d.abs().max().item(), "worst_tolerance_ratio": tol_ratio,
+            "pagg_max_abs_m": pagg_abs, "pass": bool(mpjpe_mm <= 0.1 and tol_ratio <= 1.0),
+            "note": "max_rel = max |d| / max(|ref|, 2e-2 m); worst_tolerance_ratio = max |d| / (1e-3*|ref| + 2e-5 m), "
+                    "pass iff <= 1 and mpjpe_mm <= 0.1"}
+
+
+def gpu_eager_baseline(torch, H, K, clips, our_fps):
+    """The optimisation bar BASELINE.md section 4 names: the reference algorithm as eager PyTorch CUDA ops in fp32 with
+    TF32 off (cuBLAS SGEMM) on the same B200 -- the oracle port moved to the device, never the product path."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    run, _ = cpu_lift_sample(H, K, clips=clips, device="cuda")
+    run()                                                               # warm-up (cuBLAS handles, allocator)
+    sec = min(run(), run())
+    fps = clips * FRAMES / sec
+    return {"value": fps, "unit": "frames/s", "kind": "port-on-cuda", "clips": clips, "seconds": sec,
+            "dtype": "fp32, allow_tf32=False", "speedup_of_this_repo": our_fps / fps if fps > 0 else None}
+
+
+def sharding_check(torch, pd, engine, batch, H, mode, rank, world, dev):
+    """Rank 0 recomputes, alone, what the ranks computed together and compares it with the gathered result bit for bit:
+    clip sharding -- rank 1's shard with gather=False; hypothesis sharding -- the whole lift as a 1-rank run."""
+    import torch.distributed as dist
+    x2d, x2df, traj, cam = batch
+    seed = 4242
+    res = pd.lift_sharded(engine, x2d, x2df, traj, cam, H, mode=mode, seed=seed, rank=rank, world=world)
+    out = None
+    if rank == 0:
+        B = x2d.shape[0]
+        if mode == "clips":
+            b0, b1 = pd.shard_range(B, world, 1)
+            alone = pd.lift_sharded(engine, x2d, x2df, traj, cam, H, mode=mode, seed=seed, rank=1, world=world, gather=False)
+            rows = slice(b0, b1)
+        else:
+            alone = pd.lift_sharded(engine, x2d, x2df, traj, cam, H, mode=mode, seed=seed, rank=0, world=1)
+            rows = slice(0, B)
+        out = {"mode": mode, "rows": [rows.start, rows.stop],
+               "jagg_equal": bool(torch.equal(res.jagg[rows], alone.jagg)),
+               "pagg_equal": bool(torch.equal(res.pagg[rows], alone.pagg)),
+               "select_equal": bool(torch.equal(res.select[rows], alone.select))}
+        out["pass"] = out["jagg_equal"] and out["pagg_equal"] and out["select_equal"]
+    torch.cuda.synchronize()
+    dist.barrier()
+    return out
+
+
+def single_gpu_refs():
+    path = os.path.join(ROOT, "profiles", "single_gpu_refs.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+def extra_configs(torch, dist, pd, model, engine, sk, timed, rank, world, dev, args):
+    """BASELINE.json configs[2] and configs[3] inside the same process (the driver only launches the default line):
+    cfg3 = 64 clips, num_proposals=20, sampling_timesteps=10, HYPOTHESES sharded over the ranks (strong scaling);
+    cfg4 = 512 clips per GPU (4096 on 8), H=5, K=5, CLIP sharded, one all-gather of the aggregated poses."""
+    from pafuse_b200 import synthetic
+    refs, out = single_gpu_refs(), {}
+    K0 = model.sampling_timesteps
+
+    def run_cfg(name, clips_global, H, K, mode, steps, warm):
+        x2d_h, x2df_h = synthetic.synthetic_inputs(clips_global, seed=2)
+        x2d, x2df = x2d_h.to(dev), x2df_h.to(dev)
+        traj, cam = synthetic.synthetic_trajectory(clips_global, seed=2).to(dev), synthetic.h36m_cam0_intrinsics().to(dev)
+        model.sampling_timesteps = K
+        try:
+            fn = lambda seed: pd.lift_sharded(engine, x2d, x2df, traj, cam, H, mode=mode, seed=seed, rank=rank, world=world)
+            ms = timed(fn, steps, warm)
+            chk = sharding_check(torch, pd, engine, (x2d, x2df, traj, cam), H, mode, rank, world, dev) if world > 1 else None
+        finally:
+            model.sampling_timesteps = K0
+        fps = clips_global * FRAMES / (ms * 1e-3)
+        d = {"frames_per_s": fps, "ms_per_step": ms, "steps": steps, "clips": clips_global, "num_proposals": H,
+             "sampling_timesteps": K, "sharding": mode, "n_gpus": world, "sharding_check": chk}
+        ref = refs.get(name + "_fps_1gpu")
+        if ref:
+            d["fps_1gpu_ref"] = ref
+            d["scaling_efficiency"] = fps / (ref * world)
+        out[name] = d
+
+    run_cfg("cfg3", 64, 20, 10, "hypotheses", 2, 1)
+    run_cfg("cfg4", 512 * world, 5, 5, "clips", 1, 1)
+    return out
 
 
 def main():
@@ -351,8 +487,12 @@ def main():
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU (weak scaling)")
     ap.add_argument("--proposals", type=int, default=5)
     ap.add_argument("--timesteps", type=int, default=5)
-    ap.add_argument("--cpu-clips", type=int, default=1, help="clips in the bounded CPU sample")
+    ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-CUDA leg (gpu_eager_baseline)")
+    ap.add_argument("--eager-clips", type=int, default=8, help="clips in the eager-CUDA sample")
+    ap.add_argument("--extra", action="store_true", help="also run BASELINE configs[2] / configs[3] (default when --gpus > 1)")
+    ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--max-seqs", type=int, default=0, help="sequences per workspace pass (0 = library default)")
     ap.add_argument("--shard", default="clips", choices=["clips", "hypotheses"],
                     help="clips: every GPU lifts its own --clips clips (weak scaling, the default and the driver's run); "

@@ -122,6 +122,25 @@ int pafuse_mpjpe_metrics(pafuse_ctx* ctx, const float* pred, const float* target
                          int32_t cam_per_clip, const float* x2d, const float* reproj, double* sums, int32_t B, int32_t K,
                          int32_t H, void* stream);
 
+/* Part-based variants of the same protocols (common/loss.py:114-146 `mpjpe_diffusion(part_based=True)` and :36-88
+ * `mpjpe_diffusion_all_min(mean_pos=True, part_based=True)`, both called by evaluate(), main_h3wb.py:350-362):
+ * prediction and target are centred per part first (center_pose_parts, common/utils.py:95-110).
+ * part_of_joint / root_of_joint: host arrays [num_kps] -- index of the part a joint belongs to (-1: none) and the root
+ * joint of that part (dataset.parts_joint_indices / dataset.root_indices).  sums (device, fp64) [K][H+1][n_parts]:
+ * rows h < H hold, per part, the SUM over (b,f,j in part) of the part-centred error of hypothesis h; row H the same for
+ * the mean pose over the hypotheses.  The host divides by the joint counts and picks the best hypothesis. */
+int pafuse_mpjpe_metrics_parts(pafuse_ctx* ctx, const float* pred, const float* target, const int32_t* part_of_joint,
+                               const int32_t* root_of_joint, int32_t n_parts, double* sums, int32_t B, int32_t K, int32_t H,
+                               void* stream);
+
+/* The sampler's Gaussian draws (torch.randn / randn_like at common/diffusionpose.py:283,308) as a counter-based
+ * generator, so that a rank of a multi-GPU run produces exactly ITS slice of the global (B,H,F,num_kps,3) tensor:
+ * out[r*row_len + i] = N(0,1) value of global element `base + r*row_stride + i` of draw number `draw` under `seed`
+ * (Philox4x32-10, Box-Muller in fp64).  Clip shards are one row; hypothesis shards are B rows of (h1-h0)*F*num_kps*3
+ * elements with stride H*F*num_kps*3.  The union of any sharding is bit-identical to the one-row global draw. */
+int pafuse_randn(pafuse_ctx* ctx, uint64_t seed, uint64_t draw, int64_t base, float* out, int64_t rows, int64_t row_len,
+                 int64_t row_stride, void* stream);
+
 /* ---- caller-side preparation (the code around the model call in main_h3wb.py / in_the_wild) ----
  *
  * pafuse_prepare_clips: eval_data_prepare (main_h3wb.py:122-154, in_the_wild/utils.py:279-320) fused with the flip-TTA
@@ -196,6 +215,12 @@ int pafuse_set_fuse_mlp(pafuse_ctx* ctx, int32_t enable);
  * one after the other on the caller's stream.  Results are bit-identical either way.
  * shares: SMs per part (NULL = proportional to J*C). */
 int pafuse_set_part_streams(pafuse_ctx* ctx, int32_t enable, const int32_t* shares);
+/* Small batches (CPU-plumbing config, the tail batch of a long video, a hypothesis shard of 1-2 clips) are bound by
+ * the ~1400 launches of a denoiser pass, not by the device: passes of at most `max_seqs` sequences (default 96;
+ * 0 disables) are captured into a CUDA graph per (input pointers, shape) key on their second occurrence and
+ * replayed afterwards.  pafuse_graph_replays counts the passes that ran as one graph launch. */
+int pafuse_set_graph_max_seqs(pafuse_ctx* ctx, int32_t max_seqs);
+int64_t pafuse_graph_replays(pafuse_ctx* ctx);
 /* process-wide: 2 (default) = tcgen05 CTA pairs (cta_group::2, 256-row tiles), 1 = lone CTAs */
 int pafuse_set_gemm_cta_group(int32_t cta_group);
 /* process-wide: 1 (default) = weight-stationary GEMM tiles where the W slice fits in shared memory, 0 = always stream W */

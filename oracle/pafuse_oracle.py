@@ -13,7 +13,7 @@ unmodified from /root/reference by ``oracle/ref_harness.py`` and frozen as
 ``tests/golden/*.npz`` by ``tests/golden/make_golden.py`` (script + vectors are
 committed).  ``tests/test_oracle_golden.py`` checks every function below against
 those vectors; the one reference known-answer test (``common/utils.py:129-157``)
-is restated in ``tests/test_reassembly.py``.
+is restated in ``tests/test_oracle_golden.py::test_reference_known_answer_test_of_part_functions``.
 
 Each function cites the reference lines it follows (paths relative to
 /root/reference).
@@ -387,3 +387,29 @@ def mpjpe_p_best(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     err = torch.norm(p - t[:, None, None], dim=-1)                    # b k h f j
     K, H = pred.shape[1], pred.shape[2]
     return err.permute(1, 2, 0, 3, 4).reshape(K, H, -1).mean(dim=-1).min(dim=1).values
+
+
+def mpjpe_p_best_parts(pred: torch.Tensor, target: torch.Tensor, parts_joint_indices: dict, root_indices: dict):
+    """mpjpe_diffusion(mean_pos=False, part_based=True), loss.py:119-127,135-154: both poses centred per part, the
+    hypothesis with the smallest whole-pose mean error wins, its per-part means are returned next to that minimum."""
+    p = center_pose_parts(pred, parts_joint_indices, root_indices)
+    t = center_pose_parts(target, parts_joint_indices, root_indices)
+    err = torch.norm(p - t[:, None, None], dim=-1)                    # b k h f j
+    K, H = pred.shape[1], pred.shape[2]
+    per_h = err.permute(1, 2, 0, 3, 4).reshape(K, H, -1).mean(dim=-1)
+    best, inds = per_h.min(dim=1)
+    parts = {}
+    for name, idx in parts_joint_indices.items():
+        e = err[..., idx].permute(1, 2, 0, 3, 4).reshape(K, H, -1).mean(dim=-1)
+        parts[name] = e.gather(1, inds.view(-1, 1)).squeeze(1)
+    return best, parts
+
+
+def mpjpe_p_agg_parts(pred: torch.Tensor, target: torch.Tensor, parts_joint_indices: dict, root_indices: dict):
+    """mpjpe_diffusion_all_min(mean_pos=True, part_based=True), loss.py:41-51,68-86."""
+    p = center_pose_parts(pred, parts_joint_indices, root_indices)
+    t = center_pose_parts(target, parts_joint_indices, root_indices)
+    err = torch.norm(p.mean(dim=2) - t[:, None], dim=-1)              # b k f j
+    K = pred.shape[1]
+    parts = {name: err[..., idx].permute(1, 0, 2, 3).reshape(K, -1).mean(dim=-1) for name, idx in parts_joint_indices.items()}
+    return err.permute(1, 0, 2, 3).reshape(K, -1).mean(dim=-1), parts

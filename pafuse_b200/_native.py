@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_uint64, c_void_p
 
 import torch
 
@@ -45,6 +45,11 @@ _SIGNATURES = {
                                    c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "pafuse_mpjpe_metrics": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                        c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "pafuse_mpjpe_metrics_parts": (c_int32, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), POINTER(c_int32), c_int32,
+                                             c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "pafuse_randn": (c_int32, [c_void_p, c_uint64, c_uint64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "pafuse_set_graph_max_seqs": (c_int32, [c_void_p, c_int32]),
+    "pafuse_graph_replays": (c_int64, [c_void_p]),
     "pafuse_prepare_clips": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "pafuse_stitch_clips": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "pafuse_keypoints_from_detections": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
@@ -280,7 +285,9 @@ class NativeContext:
         check(self.lib.pafuse_set_debug_simt_gemm(self.handle, 1 if enable else 0), "pafuse_set_debug_simt_gemm")
 
     def mpjpe_metrics(self, pred, target, traj, cam, x2d, reproj=None):
-        pred, target, x2d = _f32c(pred, self.device), _f32c(target, self.device), _f32c(x2d, self.device)
+        """(K, 3+H) SUMS over (b,f,j): J-Best, P-Agg, J-Agg (0 without a 2D target), per-hypothesis root-centred error."""
+        pred, target = _f32c(pred, self.device), _f32c(target, self.device)
+        x2d = None if x2d is None else _f32c(x2d, self.device)
         traj = None if traj is None else _f32c(traj, self.device)
         cam = None if cam is None else _f32c(cam, self.device)
         reproj = None if reproj is None else _f32c(reproj, self.device)
@@ -291,7 +298,35 @@ class NativeContext:
             check(self.lib.pafuse_mpjpe_metrics(self.handle, _ptr(pred), _ptr(target), _ptr(traj), _ptr(cam), cam_per_clip,
                                                 _ptr(x2d), _ptr(reproj), _ptr(sums), B, K, H, _stream()),
                   "pafuse_mpjpe_metrics")
-        return sums / float(B * F * J)
+        return sums
+
+    def mpjpe_metrics_parts(self, pred, target, part_of_joint, root_of_joint, n_parts):
+        """(K, H+1, n_parts) SUMS of the part-centred errors: rows h < H per hypothesis, row H for the mean pose."""
+        pred, target = _f32c(pred, self.device), _f32c(target, self.device)
+        B, K, H, F, J, _ = pred.shape
+        sums = torch.empty((K, H + 1, n_parts), dtype=torch.float64, device=self.device)
+        pj = (c_int32 * J)(*[int(v) for v in part_of_joint])
+        rj = (c_int32 * J)(*[int(v) for v in root_of_joint])
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_mpjpe_metrics_parts(self.handle, _ptr(pred), _ptr(target), pj, rj, n_parts, _ptr(sums),
+                                                      B, K, H, _stream()), "pafuse_mpjpe_metrics_parts")
+        return sums
+
+    def randn(self, seed, draw, base, rows, row_len, row_stride, out=None):
+        """Counter-based N(0,1) draws: element i of row r is global element ``base + r*row_stride + i`` of draw ``draw``."""
+        if out is None:
+            out = torch.empty((rows, row_len), dtype=torch.float32, device=self.device)
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == rows * row_len
+        with torch.cuda.device(self.device):
+            check(self.lib.pafuse_randn(self.handle, int(seed) & 0xFFFFFFFFFFFFFFFF, int(draw), int(base), _ptr(out),
+                                        int(rows), int(row_len), int(row_stride), _stream()), "pafuse_randn")
+        return out
+
+    def set_graph_max_seqs(self, max_seqs: int):
+        check(self.lib.pafuse_set_graph_max_seqs(self.handle, int(max_seqs)), "pafuse_set_graph_max_seqs")
+
+    def graph_replays(self) -> int:
+        return int(self.lib.pafuse_graph_replays(self.handle))
 
     # ---- caller-side preparation
     def prepare_clips(self, seq, want_flip=True):

@@ -148,10 +148,11 @@ static int launch_one(const AttnParams& p, cudaStream_t st) {
     constexpr int HDP = (HD % 32 == 0) ? HD + 4 : HD;
     size_t smem = (size_t)2 * L * HPC * HDP * sizeof(float);
     auto kern = attention_kernel<L, HD, HPC, TEMPORAL>;
-    static bool configured = false;                          // per template instance
-    if (!configured) {
+    static bool configured[MAX_DEVICES] = {false};           // per template instance and per device
+    const int dev = current_device_slot();
+    if (!configured[dev]) {
         PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[dev] = true;
     }
     long long groups = TEMPORAL ? (long long)p.S * p.J : (long long)p.S * p.F;
     dim3 grid((unsigned)groups, 8 / HPC);

@@ -530,7 +530,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
-int g_sms = 0;
 int g_n_acc_cap = 1;     // PAFUSE_ATT_NACC: O accumulators per stage the PV passes are spread over (measured: 1 is fastest, the extra tensor-memory reads cost more than the shorter MMA chains save)
 int g_sep_mode = 1;      // PAFUSE_ATT_SEP: 0 aliased layout only, 1 separate when it fits (default), 2 also with one group less per tile (slower: measured)
 
@@ -544,9 +543,6 @@ int att_init() {
         return -2;
     }
     g_enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-    int dev = 0;
-    PAFUSE_CUDA_OK(cudaGetDevice(&dev));
-    PAFUSE_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("PAFUSE_ATT_SEP")) g_sep_mode = atoi(e);
     if (const char* e = getenv("PAFUSE_ATT_NACC")) g_n_acc_cap = atoi(e);
     return 0;
@@ -593,16 +589,17 @@ int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& 
         return -1;
     }
     auto kern = attention_tc_kernel<HDP, LT, SEP>;
-    static int configured = 0;
-    if (configured < SMEM) {
+    static int configured[MAX_DEVICES] = {0};                          // per template instance and per device
+    const int dev = current_device_slot();
+    if (configured[dev] < SMEM) {
         PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        configured = SMEM;
+        configured[dev] = SMEM;
     }
     const long long units = (long long)p.num_tiles * 8;
     int grid = (int)(units < sms ? units : sms);
     // on an SM share the CTAs are placed as pairs (no cluster feature is used), so that the share keeps whole
     // TPCs and the CTA pairs of the GEMMs running next to it on other streams still find two free SMs together
-    const int cluster = sms < g_sms && grid % 2 == 0 ? 2 : 1;
+    const int cluster = sms < device_sm_count() && grid % 2 == 0 ? 2 : 1;
     PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(ATT_THREADS), (size_t)SMEM, st, cluster, mh, ml, p));
     PAFUSE_LAUNCH_OK();
     return 0;
@@ -614,7 +611,8 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
                         cudaStream_t st, int sm_limit) {
     if (S == 0) return 0;
     if (int rc = att_init()) return rc;
-    const int sms = sm_limit > 0 && sm_limit < g_sms ? sm_limit : g_sms;
+    const int num_sms = device_sm_count();
+    const int sms = sm_limit > 0 && sm_limit < num_sms ? sm_limit : num_sms;
     const int hd = C / 8, hds = attn_head_store(hd), hdp = hds > 32 ? 64 : 32;
     const int L = temporal ? F : J;
     if (hd > 64 || hd % 4 != 0 || L > 128 || pl.hds != hds || pl.rows_cap != (long long)S * F * J) {

@@ -36,6 +36,27 @@ extern thread_local long long g_launch_count;  // kernels launched by this libra
         }                                                                                 \
     } while (0)
 
+// ---------------------------------------------------------------- per-device state
+// Function attributes (the dynamic shared-memory opt-in) and the SM count belong to a DEVICE, not to the process:
+// a context may be created on cuda:1 after cuda:0 was used (one process driving several GPUs, the reference's
+// nn.DataParallel mode).  Everything that was a process-wide "configured" flag is indexed by the current device.
+constexpr int MAX_DEVICES = 64;
+inline int current_device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+    return d;
+}
+inline int device_sm_count() {
+    static int sms[MAX_DEVICES] = {0};
+    const int d = current_device_slot();
+    if (sms[d] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 1;
+        sms[d] = v;
+    }
+    return sms[d];
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // Every kernel of the denoiser chain is launched with programmaticStreamSerialization and runs
 //   pdl_launch_dependents();  ... set-up that touches no global data ...  pdl_wait();
@@ -88,7 +109,7 @@ constexpr float WEIGHT_SCALE = 256.0f;
 constexpr float WEIGHT_UNSCALE = 1.0f / 256.0f;
 
 __device__ __forceinline__ void split_op(float v, op_t& hi, op_t& lo) {
-    v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+    v = v != v ? v : fminf(fmaxf(v, -65504.0f), 65504.0f);      // saturate, but let a NaN stay a NaN like the fp32 reference
     hi = __float2half_rn(v);
     lo = __float2half_rn(v - __half2float(hi));
 }

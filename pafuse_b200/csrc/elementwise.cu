@@ -685,8 +685,9 @@ __global__ void metrics_kernel(AggParams p, const float* __restrict__ target, co
     const float* g = target + (((size_t)b * p.F + f) * p.J + j) * 3;
     const float* g0 = target + (((size_t)b * p.F + f) * p.J) * 3;    // root joint of the frame
     const float* tr = p.traj ? p.traj + ((size_t)b * p.F + f) * 3 : nullptr;
-    const float* tgt2 = p.x2d + (((size_t)b * p.F + f) * p.J + j) * 2;
-    const float* cam = p.cam + (p.cam_per_clip ? b * 9 : 0);
+    const bool has2d = p.x2d != nullptr;                            // without a 2D target the J-Agg column is not meaningful (0)
+    const float* tgt2 = has2d ? p.x2d + (((size_t)b * p.F + f) * p.J + j) * 2 : nullptr;
+    const float* cam = p.cam ? p.cam + (p.cam_per_clip ? b * 9 : 0) : nullptr;
     float gv[3] = {0.f, 0.f, 0.f}, gc[3] = {0.f, 0.f, 0.f}, sum[3] = {0.f, 0.f, 0.f};
     if (live) {
 #pragma unroll
@@ -713,20 +714,22 @@ __global__ void metrics_kernel(AggParams p, const float* __restrict__ target, co
             }
             const float e = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
             e_c = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dc[0], dc[0]), __fmul_rn(dc[1], dc[1])), __fmul_rn(dc[2], dc[2])));
-            float uv[2];
-            if (reproj_in) {
-                const float* r2 = reproj_in + (base + j) * 2;
-                uv[0] = r2[0];
-                uv[1] = r2[1];
-            } else {
-                project_point(xa, cam, uv);
-            }
-            const float d0 = __fsub_rn(uv[0], tgt2[0]), d1 = __fsub_rn(uv[1], tgt2[1]);
-            const float e2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));
             if (h == 0 || e < jbest) jbest = e;
-            if (h == 0 || e2 < best2d) {
-                best2d = e2;
-                jagg = e;
+            if (has2d) {
+                float uv[2];
+                if (reproj_in) {
+                    const float* r2 = reproj_in + (base + j) * 2;
+                    uv[0] = r2[0];
+                    uv[1] = r2[1];
+                } else {
+                    project_point(xa, cam, uv);
+                }
+                const float d0 = __fsub_rn(uv[0], tgt2[0]), d1 = __fsub_rn(uv[1], tgt2[1]);
+                const float e2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));
+                if (h == 0 || e2 < best2d) {
+                    best2d = e2;
+                    jagg = e;
+                }
             }
         }
         // per-hypothesis sum of the root-centred error over the block
@@ -764,6 +767,133 @@ int launch_metrics(const AggParams& p, const float* target, const float* reproj_
     dim3 grid((unsigned)((p.F * p.J + threads - 1) / threads), (unsigned)(p.B * p.K));
     const size_t smem = (size_t)(3 + p.H) * (threads / 32) * sizeof(double);
     metrics_kernel<<<grid, threads, smem, st>>>(p, target, reproj_in, out);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// Part-based variants of P-Best and P-Agg (common/loss.py:114-146 and :36-88 with part_based=True; evaluate() calls both,
+// main_h3wb.py:350-362): prediction and target are centred PER PART first (center_pose_parts, common/utils.py:95-110:
+// joint j of part p minus the part's root joint), then
+//   out[k][h][p] (h < H)  = sum over (b, f, j in p) of |pc - gc| of hypothesis h      (P-Best part-based: the host takes the
+//                                                                                    hypothesis with the smallest total)
+//   out[k][H][p]          = sum over (b, f, j in p) of |mean_h pc - gc|               (P-Agg part-based)
+// One thread per (b, k, f, j); block partial sums (fp64) in shared memory, then one atomicAdd per (h, part) and block.
+__global__ void metrics_parts_kernel(AggParams p, const float* __restrict__ target, const int* __restrict__ part_of_joint,
+                                     const int* __restrict__ root_of_joint, int n_parts, double* __restrict__ out) {
+    const int bk = blockIdx.y;
+    const int k = bk % p.K;
+    const long long b = bk / p.K;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;          // (f, j)
+    const int FJ = p.F * p.J;
+    extern __shared__ double red[];                                   // [(H + 1)][n_parts]
+    const int nred = (p.H + 1) * n_parts;
+    for (int i = threadIdx.x; i < nred; i += blockDim.x) red[i] = 0.0;
+    __syncthreads();
+    const int f = item < FJ ? item / p.J : 0, j = item < FJ ? item % p.J : 0;
+    const int part = item < FJ ? part_of_joint[j] : -1;
+    if (part >= 0) {
+        const int r = root_of_joint[j];
+        const float* g = target + (((size_t)b * p.F + f) * p.J) * 3;
+        float gc[3], sum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gc[c] = __fsub_rn(g[j * 3 + c], g[r * 3 + c]);
+        for (int h = 0; h < p.H; ++h) {
+            const float* x = p.pred + (((((size_t)b * p.K + k) * p.H + h) * p.F + f) * p.J) * 3;
+            float d[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float pc = __fsub_rn(x[j * 3 + c], x[r * 3 + c]);
+                d[c] = __fsub_rn(pc, gc[c]);
+                sum[c] = h == 0 ? pc : __fadd_rn(sum[c], pc);
+            }
+            const float e = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+            atomicAdd(&red[h * n_parts + part], (double)e);
+        }
+        const float hf = (float)p.H;
+        float m[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) m[c] = __fsub_rn(__fdiv_rn(sum[c], hf), gc[c]);
+        const float e = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], m[0]), __fmul_rn(m[1], m[1])), __fmul_rn(m[2], m[2])));
+        atomicAdd(&red[p.H * n_parts + part], (double)e);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nred; i += blockDim.x) atomicAdd(out + (size_t)k * nred + i, red[i]);
+}
+
+int launch_metrics_parts(const AggParams& p, const float* target, const int* part_of_joint, const int* root_of_joint,
+                         int n_parts, double* out, cudaStream_t st) {
+    if ((long long)p.B * p.K == 0) return 0;
+    const int threads = 256;
+    dim3 grid((unsigned)((p.F * p.J + threads - 1) / threads), (unsigned)(p.B * p.K));
+    const size_t smem = (size_t)(p.H + 1) * n_parts * sizeof(double);
+    metrics_parts_kernel<<<grid, threads, smem, st>>>(p, target, part_of_joint, root_of_joint, n_parts, out);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ counter-based Gaussian noise (multi-GPU sampler draws)
+// The sampler's draws (diffusionpose.py:283, :308) as a pure function of (seed, draw, element index): element e of draw
+// `stream_id` is Box-Muller of the Philox4x32-10 block with counter (e >> 1, stream_id) and key = seed, cosine branch,
+// using words (0,1) for even e and (2,3) for odd e.  Any rank can therefore generate exactly its slice of the global
+// (B,H,F,J,3) tensor -- no rank draws the whole tensor to keep a slice, and the union of the shards is bit-identical to
+// the single-GPU draw whatever the sharding.  The transform runs in fp64 (one rounding to fp32 at the end), which makes
+// the values reproducible to the last bit against a numpy restatement (tests/test_host_logic.py).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void randn_philox_kernel(float* __restrict__ out, unsigned long long seed, unsigned long long stream_id,
+                                    long long base, long long rows, long long row_len, long long row_stride) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * row_len) return;
+    const long long r = i / row_len;
+    const unsigned long long e = (unsigned long long)(base + r * row_stride + (i - r * row_len));
+    const unsigned long long ctr = e >> 1;
+    uint32_t w[4];
+    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), w);
+    const uint32_t a = w[2 * (e & 1)], b2 = w[2 * (e & 1) + 1];
+    const double u1 = ((double)a + 0.5) * (1.0 / 4294967296.0);      // (0, 1)
+    const double u2 = ((double)b2 + 0.5) * (1.0 / 4294967296.0);
+    out[i] = (float)(sqrt(-2.0 * log(u1)) * cospi(2.0 * u2));
+}
+
+int launch_randn_philox(float* out, unsigned long long seed, unsigned long long stream_id, long long base, long long rows,
+                        long long row_len, long long row_stride, cudaStream_t st) {
+    const long long total = rows * row_len;
+    if (total == 0) return 0;
+    randn_philox_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, seed, stream_id, base, rows, row_len, row_stride);
+    PAFUSE_LAUNCH_OK();
+    return 0;
+}
+
+// max |w| of a GEMM weight tensor, as the bit pattern of a non-negative float (monotone under atomicMax on unsigned);
+// a NaN compares as larger than everything finite, which is what the range check wants.
+__global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned int* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned int m = 0u;
+    for (; i < n; i += stride) m = max(m, __float_as_uint(w[i]) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+int launch_absmax(const float* w, size_t n, unsigned int* out, cudaStream_t st) {
+    if (n == 0) return 0;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    absmax_kernel<<<blocks, 256, 0, st>>>(w, n, out);
     PAFUSE_LAUNCH_OK();
     return 0;
 }

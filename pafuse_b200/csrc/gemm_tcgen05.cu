@@ -1056,7 +1056,6 @@ int make_map_planes(CUtensorMap* map, const void* ptr, long long rows_cap, int h
     return 0;
 }
 
-int g_num_sms = 0;
 int g_force_cg = 0;      // PAFUSE_GEMM_CTA_GROUP=1|2 overrides the default (2)
 int g_wres_enabled = 1;  // PAFUSE_GEMM_WRES=0 disables the weight-stationary mode
 int g_wres_min_stages = 4;  // with 3 stages (C = 384) the resident mode was slower than streaming (profiles/r1g_*)
@@ -1066,13 +1065,14 @@ int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
                const CUtensorMap& o0, const CUtensorMap& o1, const CUtensorMap& o2, const KernelParams& kp, int grid,
                int smem, cudaStream_t st) {
     auto kern = gemm_f16x3_kernel<EPI, CG, WRES>;
-    static bool configured = false;                                   // per template instance
-    if (!configured) {
+    static bool configured[MAX_DEVICES] = {false};                    // per template instance and per device
+    const int dev = current_device_slot();
+    if (!configured[dev]) {
         cudaFuncAttributes fa;
         PAFUSE_CUDA_OK(cudaFuncGetAttributes(&fa, kern));              // static shared memory counts against the 227 KiB
         PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             SMEM_LIMIT - (int)fa.sharedSizeBytes));
-        configured = true;
+        configured[dev] = true;
     }
     PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(NUM_THREADS), (size_t)smem, st, CG, ah, al, wh, wl, o0, o1,
                                 o2, kp));
@@ -1114,7 +1114,8 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
             return -1;
         }
     }
-    const int sms = g.sm_limit > 0 && g.sm_limit < g_num_sms ? g.sm_limit : g_num_sms;
+    const int num_sms = device_sm_count();
+    const int sms = g.sm_limit > 0 && g.sm_limit < num_sms ? g.sm_limit : num_sms;
     const int max_groups = sms / CG > 0 ? sms / CG : 1;
     const int WN = BN / CG;
     const int slack = g.epilogue == EPI_RESID_LN ? SMEM_SLACK_LN : SMEM_SLACK;
@@ -1216,13 +1217,16 @@ int launch_mlp(const MlpArgs& g, cudaStream_t st) {
     mp.ep.ln = g.ln;
 
     auto kern = mlp_fused_kernel;
-    static int max_dyn = 0;
-    if (!max_dyn) {
+    static int max_dyn_dev[MAX_DEVICES] = {0};                         // per device (function attributes are per device)
+    const int dev = current_device_slot();
+    if (!max_dyn_dev[dev]) {
         cudaFuncAttributes fa;
         PAFUSE_CUDA_OK(cudaFuncGetAttributes(&fa, kern));
-        max_dyn = SMEM_LIMIT - (int)fa.sharedSizeBytes;
-        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            SMEM_LIMIT - (int)fa.sharedSizeBytes));
+        max_dyn_dev[dev] = SMEM_LIMIT - (int)fa.sharedSizeBytes;
     }
+    const int max_dyn = max_dyn_dev[dev];
     const int fixed = 1024 + mp.kb * 2 * MLP_A_BOX_BYTES + STG_BYTES;
     int stages = (max_dyn - fixed) / MLP_STAGE_BYTES;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -1243,7 +1247,8 @@ int launch_mlp(const MlpArgs& g, cudaStream_t st) {
     if (int rc = make_map_out(&ox, g.x, g.M, C, true)) return rc;
     if (int rc = make_map_out(&oh, g.out_hi, g.M, C, false)) return rc;
     if (int rc = make_map_out(&ol, g.out_lo, g.M, C, false)) return rc;
-    const int sms = g.sm_limit > 0 && g.sm_limit < g_num_sms ? g.sm_limit : g_num_sms;
+    const int num_sms = device_sm_count();
+    const int sms = g.sm_limit > 0 && g.sm_limit < num_sms ? g.sm_limit : num_sms;
     const int max_pairs = sms / 2 > 0 ? sms / 2 : 1;
     const int grid = 2 * (mp.m_tiles < max_pairs ? mp.m_tiles : max_pairs);
     PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(NUM_THREADS), (size_t)smem, st, 2, ah, al, w1h, w1l, w2h, w2l,
@@ -1286,9 +1291,6 @@ int gemm_init() {
         return -2;
     }
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-    int dev = 0;
-    PAFUSE_CUDA_OK(cudaGetDevice(&dev));
-    PAFUSE_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     const char* e = getenv("PAFUSE_GEMM_CTA_GROUP");
     g_force_cg = e ? atoi(e) : 0;
     if (const char* w = getenv("PAFUSE_GEMM_WRES")) g_wres_enabled = atoi(w);

@@ -164,6 +164,11 @@ int launch_stitch_clips(const float* pred, float* out, long long n_clips, int K,
                         cudaStream_t st);
 int launch_metrics(const AggParams& p, const float* target, const float* reproj_in, double* out, cudaStream_t st);
 int launch_keypoints(const float* raw, float* kp, long long T, int J, int w, int h, cudaStream_t st);
+int launch_metrics_parts(const AggParams& p, const float* target, const int* part_of_joint, const int* root_of_joint,
+                         int n_parts, double* out, cudaStream_t st);
+int launch_randn_philox(float* out, unsigned long long seed, unsigned long long stream_id, long long base, long long rows,
+                        long long row_len, long long row_stride, cudaStream_t st);
+int launch_absmax(const float* w, size_t n, unsigned int* out, cudaStream_t st);
 int launch_attention(const AttnParams& p, cudaStream_t st);          // CUDA-core version (debug reference)
 int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int F, int J, int C, int temporal,
                         cudaStream_t st, int sm_limit = 0);

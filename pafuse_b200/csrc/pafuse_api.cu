@@ -22,6 +22,7 @@ thread_local long long g_launch_count = 0;
 // (profiles/r1n_*), and it is suspended while the parts run side by side on SM shares, where early-resident CTAs
 // of a dependent kernel would squat on SMs of another part's share.
 thread_local int g_pdl_suspend = 0;
+int g_switch_epoch = 0;   // bumped by the process-wide GEMM switches: captured passes of every context become stale
 bool pdl_enabled() {
     static const bool on = [] {
         const char* e = getenv("PAFUSE_PDL");
@@ -58,6 +59,20 @@ struct Part {
     const float* w(const std::string& n) const { return f32 + slots.at(n).off; }
     const op_t* wh(const std::string& n) const { return hi + slots.at(n).off; }
     const op_t* wl(const std::string& n) const { return lo + slots.at(n).off; }
+};
+
+// key of a captured denoiser pass: every pointer and shape the captured launches depend on
+struct GraphKey {
+    const void *x2d, *x2d_flip, *x3d, *sinus, *pred;
+    int apply_clamp, R, H, S_total;
+    bool operator<(const GraphKey& o) const {
+        return memcmp(this, &o, sizeof(GraphKey)) < 0;
+    }
+};
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0;                    // direct runs so far (the first one allocates and configures: never captured)
+    long long launches = 0;          // kernel nodes of the graph
 };
 
 struct Workspace {
@@ -108,8 +123,20 @@ struct pafuse_ctx {
     int num_parts = 0;
     Part parts[PAFUSE_MAX_PARTS];
     int* flip_perm_dev = nullptr;
-    int* conn_dev = nullptr;         // scratch for wb_pose_from_parts tables
+    int* conn_dev = nullptr;         // wb_pose_from_parts tables, resident: uploaded when the caller's table changes
     int* conn_rows_dev = nullptr;
+    std::vector<int> conn_host, conn_rows_host;
+    int* part_of_joint_dev = nullptr;   // part-based metrics tables, resident the same way
+    int* root_of_joint_dev = nullptr;
+    std::vector<int> part_of_joint_host, root_of_joint_host;
+    unsigned int* absmax_dev = nullptr; // range check of the GEMM weights at commit
+    // Small-R path: below graph_max_seqs sequences per pass the ~1400 launches of a denoiser pass cost more on the
+    // host than on the device, so a pass is captured once per (inputs, shape) key into a CUDA graph and replayed.
+    std::map<GraphKey, GraphEntry> graphs;
+    int graph_max_seqs = 96;         // PAFUSE_GRAPH_MAX_SEQS (0 disables); the bench shapes (640 sequences) never capture
+    cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the caller's may be the legacy default stream)
+    long long graph_replays = 0;
+    int graph_epoch = 0;
     Workspace ws[PAFUSE_MAX_PARTS];  // [0] serves every part in the sequential mode; one per part when they run side by side
     // side-by-side mode: the part denoisers are independent until the DDIM update, so each runs on its own stream
     // on a share of the SMs (persistent kernels sized to the share); the HBM-bound kernels of one part (proj, fc2,
@@ -214,8 +241,16 @@ int dev_alloc(T** p, size_t n) {
     return 0;
 }
 
+// captured passes hold workspace / prediction pointers and the switches of the context: drop them when any of it changes
+void drop_graphs(pafuse_ctx* ctx) {
+    for (auto& kv : ctx->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    ctx->graphs.clear();
+}
+
 int ensure_workspace(pafuse_ctx* ctx, Workspace& w, long long rows_x_c) {
     if (rows_x_c <= w.rows_x_c) return 0;
+    drop_graphs(ctx);
     cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv); cudaFree(w.pl_hi); cudaFree(w.pl_lo);
     cudaFree(w.o_hi); cudaFree(w.o_lo); cudaFree(w.h_hi); cudaFree(w.h_lo);
     w = Workspace();
@@ -234,6 +269,7 @@ int ensure_workspace(pafuse_ctx* ctx, Workspace& w, long long rows_x_c) {
 
 int ensure_pred(pafuse_ctx* ctx, size_t floats) {
     if (floats <= ctx->pred_cap) return 0;
+    drop_graphs(ctx);
     cudaFree(ctx->pred);
     ctx->pred = nullptr;
     ctx->pred_cap = 0;
@@ -544,6 +580,73 @@ int run_denoisers(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, cons
     return rc;
 }
 
+// run_denoisers, replayed from a CUDA graph when the pass is small enough to be launch-bound.  First call with a key:
+// direct (it may allocate workspaces and set function attributes, neither of which can be captured); second call:
+// captured on the context's private stream, instantiated and launched; afterwards: one cudaGraphLaunch per pass.
+int run_denoisers_cached(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, const float* x3d, int apply_clamp, int R,
+                         int H, int S_total, const float* sinus, float* pred, cudaStream_t st) {
+    const bool eligible = ctx->graph_max_seqs > 0 && S_total <= ctx->graph_max_seqs && !ctx->prof.on && !ctx->part_streams &&
+                          ctx->committed;
+    if (!eligible) return run_denoisers(ctx, x2d, x2d_flip, x3d, apply_clamp, R, H, S_total, sinus, pred, st);
+    if (ctx->graph_epoch != g_switch_epoch) {
+        drop_graphs(ctx);
+        ctx->graph_epoch = g_switch_epoch;
+    }
+    GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.x2d = x2d; key.x2d_flip = x2d_flip; key.x3d = x3d; key.sinus = sinus; key.pred = pred;
+    key.apply_clamp = apply_clamp; key.R = R; key.H = H; key.S_total = S_total;
+    if (ctx->graphs.size() > 64 && ctx->graphs.find(key) == ctx->graphs.end()) drop_graphs(ctx);   // bound the cache
+    GraphEntry& e = ctx->graphs[key];
+    if (e.exec) {
+        PAFUSE_CUDA_OK(cudaGraphLaunch(e.exec, st));
+        g_launch_count += e.launches;
+        ++ctx->graph_replays;
+        return 0;
+    }
+    if (e.seen++ == 0) return run_denoisers(ctx, x2d, x2d_flip, x3d, apply_clamp, R, H, S_total, sinus, pred, st);
+    if (!ctx->cap_stream) PAFUSE_CUDA_OK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+    const long long before = g_launch_count;
+    PAFUSE_CUDA_OK(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_denoisers(ctx, x2d, x2d_flip, x3d, apply_clamp, R, H, S_total, sinus, pred, ctx->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &graph);
+    const long long captured = g_launch_count - before;
+    g_launch_count = before;                                    // nothing ran yet
+    if (rc != 0 || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->graphs.erase(key);
+        if (rc != 0) return rc;
+        // capture refused (e.g. a first-use attribute call slipped in): run directly, try again next time
+        return run_denoisers(ctx, x2d, x2d_flip, x3d, apply_clamp, R, H, S_total, sinus, pred, st);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || !exec) {
+        cudaGetLastError();
+        ctx->graphs.erase(key);
+        return run_denoisers(ctx, x2d, x2d_flip, x3d, apply_clamp, R, H, S_total, sinus, pred, st);
+    }
+    e.exec = exec;
+    e.launches = captured;
+    PAFUSE_CUDA_OK(cudaGraphLaunch(exec, st));
+    g_launch_count += captured;
+    ++ctx->graph_replays;
+    return 0;
+}
+
+// resident copy of a small host table: uploaded only when its contents change (the upload reads pageable memory and
+// therefore drains the stream first -- once per table, not once per call)
+int sync_table(std::vector<int>& host, int* dev, const int* src, int n, cudaStream_t st) {
+    if ((int)host.size() == n && memcmp(host.data(), src, (size_t)n * sizeof(int)) == 0) return 0;
+    host.assign(src, src + n);
+    PAFUSE_CUDA_OK(cudaMemcpyAsync(dev, host.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    PAFUSE_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 bool check_ctx(pafuse_ctx* ctx) {
     if (!ctx) {
         set_last_error("null context");
@@ -604,7 +707,8 @@ int pafuse_create(const pafuse_config* cfg, pafuse_ctx** out) {
         ctx->cfg.part_joints[pi] = nullptr;   // host pointer not retained
     }
     if (dev_alloc(&ctx->flip_perm_dev, (size_t)cfg->num_kps) || dev_alloc(&ctx->conn_dev, (size_t)cfg->num_kps) ||
-        dev_alloc(&ctx->conn_rows_dev, (size_t)cfg->num_kps))
+        dev_alloc(&ctx->conn_rows_dev, (size_t)cfg->num_kps) || dev_alloc(&ctx->part_of_joint_dev, (size_t)cfg->num_kps) ||
+        dev_alloc(&ctx->root_of_joint_dev, (size_t)cfg->num_kps) || dev_alloc(&ctx->absmax_dev, (size_t)1))
         return PAFUSE_E_CUDA;
     PAFUSE_CUDA_OK(cudaMemcpy(ctx->flip_perm_dev, cfg->flip_perm, cfg->num_kps * sizeof(int), cudaMemcpyHostToDevice));
     ctx->cfg.flip_perm = nullptr;
@@ -612,6 +716,7 @@ int pafuse_create(const pafuse_config* cfg, pafuse_ctx** out) {
     if (const char* e = getenv("PAFUSE_FUSE_LN")) ctx->fuse_ln = atoi(e) != 0;
     if (const char* e = getenv("PAFUSE_PART_STREAMS")) ctx->part_streams = atoi(e) != 0;
     if (const char* e = getenv("PAFUSE_FUSE_MLP")) ctx->fuse_mlp = atoi(e) != 0;
+    if (const char* e = getenv("PAFUSE_GRAPH_MAX_SEQS")) ctx->graph_max_seqs = atoi(e);
     *out = ctx;
     return 0;
 }
@@ -626,6 +731,9 @@ void pafuse_destroy(pafuse_ctx* ctx) {
         cudaFree(w.x); cudaFree(w.a_hi); cudaFree(w.a_lo); cudaFree(w.qkv); cudaFree(w.pl_hi); cudaFree(w.pl_lo);
         cudaFree(w.o_hi); cudaFree(w.o_lo); cudaFree(w.h_hi); cudaFree(w.h_lo);
     }
+    drop_graphs(ctx);
+    if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
+    cudaFree(ctx->part_of_joint_dev); cudaFree(ctx->root_of_joint_dev); cudaFree(ctx->absmax_dev);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (int pi = 0; pi < PAFUSE_MAX_PARTS; ++pi) {
         if (ctx->side[pi]) cudaStreamDestroy(ctx->side[pi]);
@@ -680,13 +788,29 @@ int pafuse_commit_weights(pafuse_ctx* ctx, void* stream) {
                                              attn_head_store(p.C / 8), st))
                     return rc;
             }
+        // fp16 range of the pre-scaled operands: |w| * WEIGHT_SCALE must stay below 65504, else the hi half would
+        // saturate silently (the fp32 reference has no such limit).  NaN weights pass: they propagate as NaN.
+        PAFUSE_CUDA_OK(cudaMemsetAsync(ctx->absmax_dev, 0, sizeof(unsigned int), st));
         for (auto& kv : p.slots) {
-            if (kv.second.gemm)
+            if (kv.second.gemm) {
+                if (int rc = launch_absmax(p.f32 + kv.second.off, kv.second.numel, ctx->absmax_dev, st)) return rc;
                 if (int rc = launch_split_weights(p.f32 + kv.second.off, p.hi + kv.second.off, p.lo + kv.second.off,
                                                   kv.second.numel, st))
                     return rc;
+            }
+        }
+        unsigned int bits = 0;
+        PAFUSE_CUDA_OK(cudaMemcpyAsync(&bits, ctx->absmax_dev, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        PAFUSE_CUDA_OK(cudaStreamSynchronize(st));
+        float amax;
+        memcpy(&amax, &bits, sizeof(amax));
+        if (amax == amax && amax * WEIGHT_SCALE > 65504.0f) {
+            set_last_error("pafuse_commit_weights: part %d has a GEMM weight of magnitude %g; the f16x3 operand format holds "
+                           "|w| < %g", pi, (double)amax, (double)(65504.0f / WEIGHT_SCALE));
+            return PAFUSE_E_ARG;
         }
     }
+    drop_graphs(ctx);
     ctx->committed = true;
     return 0;
 }
@@ -700,7 +824,7 @@ int pafuse_pred_parts(pafuse_ctx* ctx, const float* x2d, const float* x3d, const
         return PAFUSE_E_ARG;
     }
     if (B == 0) return 0;
-    return run_denoisers(ctx, x2d, nullptr, x3d, 0, B * H, H, B * H, sinus, out, (cudaStream_t)stream);
+    return run_denoisers_cached(ctx, x2d, nullptr, x3d, 0, B * H, H, B * H, sinus, out, (cudaStream_t)stream);
 }
 
 int pafuse_ddim_step(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, const float* sinus, float* img,
@@ -719,7 +843,7 @@ int pafuse_ddim_step(pafuse_ctx* ctx, const float* x2d, const float* x2d_flip, c
     const int R = B * H;
     const int S_total = flip ? 2 * R : R;
     if (int rc = ensure_pred(ctx, (size_t)S_total * cfg.frames * cfg.num_kps * 3)) return rc;
-    if (int rc = run_denoisers(ctx, x2d, x2d_flip, img, 1, R, H, S_total, sinus, ctx->pred, st)) return rc;
+    if (int rc = run_denoisers_cached(ctx, x2d, x2d_flip, img, 1, R, H, S_total, sinus, ctx->pred, st)) return rc;
     DdimParams d;
     d.R = R; d.F = cfg.frames; d.H = H; d.num_kps = cfg.num_kps; d.flip = flip ? 1 : 0; d.last = last ? 1 : 0;
     d.pred = ctx->pred; d.flip_perm = ctx->flip_perm_dev; d.img = img; d.noise = noise;
@@ -740,6 +864,7 @@ int pafuse_wb_pose_from_parts(pafuse_ctx* ctx, float* pose, float* out, const in
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int nk = ctx->cfg.num_kps;
+    if (poses == 0) return 0;
     std::vector<int> rows;
     for (int g = 0; g < nk; ++g) {
         int r = conn_of_joint[g];
@@ -751,17 +876,17 @@ int pafuse_wb_pose_from_parts(pafuse_ctx* ctx, float* pose, float* out, const in
         for (int v : rows) seen |= (v == r);
         if (r >= 0 && !seen) rows.push_back(r);
     }
-    PAFUSE_CUDA_OK(cudaMemcpyAsync(ctx->conn_dev, conn_of_joint, nk * sizeof(int), cudaMemcpyHostToDevice, st));
+    // the tables are constant per dataset: resident on the device, re-uploaded (with the one stream drain that reading
+    // pageable memory costs) only when the caller passes a different table
+    if (int rc = sync_table(ctx->conn_host, ctx->conn_dev, conn_of_joint, nk, st)) return rc;
     {
         ProfScope ps(ctx, CAT_POST, 8.0 * (double)poses * nk * 3, st);
         if (int rc = launch_reassemble(pose, out, ctx->conn_dev, poses, nk, st)) return rc;
     }
     if (mutate_input && !rows.empty()) {
-        PAFUSE_CUDA_OK(cudaMemcpyAsync(ctx->conn_rows_dev, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (int rc = sync_table(ctx->conn_rows_host, ctx->conn_rows_dev, rows.data(), (int)rows.size(), st)) return rc;
         if (int rc = launch_negate_rows(pose, ctx->conn_rows_dev, (int)rows.size(), poses, nk, st)) return rc;
     }
-    // the two small table uploads read pageable host memory: make them complete before returning
-    PAFUSE_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -796,12 +921,13 @@ int pafuse_mpjpe_metrics(pafuse_ctx* ctx, const float* pred, const float* target
                          int32_t cam_per_clip, const float* x2d, const float* reproj, double* sums, int32_t B, int32_t K,
                          int32_t H, void* stream) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
-    if (!pred || !target || !x2d || !sums || (!reproj && !cam) || B < 0 || K < 1 || H < 1 || H > 256 || (long long)B * K > 65535) {
-        set_last_error("pafuse_mpjpe_metrics: bad argument (B*K <= 65535, H <= 256)");
+    if (!pred || !target || !sums || (x2d && !reproj && !cam) || B < 0 || K < 1 || H < 1 || H > 256 || (long long)B * K > 65535) {
+        set_last_error("pafuse_mpjpe_metrics: bad argument (B*K <= 65535, H <= 256; a 2D target needs reproj or cam)");
         return PAFUSE_E_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
     PAFUSE_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)K * (3 + H) * sizeof(double), st));
+    if (B == 0) return 0;
     AggParams a;
     a.B = B; a.K = K; a.H = H; a.F = ctx->cfg.frames; a.J = ctx->cfg.num_kps; a.cam_per_clip = cam_per_clip;
     a.pred = pred; a.traj = traj; a.cam = cam; a.x2d = x2d; a.jagg = nullptr; a.pagg = nullptr; a.select = nullptr;
@@ -809,6 +935,57 @@ int pafuse_mpjpe_metrics(pafuse_ctx* ctx, const float* pred, const float* target
     ProfScope ps(ctx, CAT_POST, 12.0 * a.F * a.J * ((double)B * K * H + B), st);
     return launch_metrics(a, target, reproj, sums, st);
 }
+
+int pafuse_mpjpe_metrics_parts(pafuse_ctx* ctx, const float* pred, const float* target, const int32_t* part_of_joint,
+                               const int32_t* root_of_joint, int32_t n_parts, double* sums, int32_t B, int32_t K, int32_t H,
+                               void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    const int nk = ctx->cfg.num_kps;
+    if (!pred || !target || !part_of_joint || !root_of_joint || !sums || n_parts < 1 || n_parts > 16 || B < 0 || K < 1 ||
+        H < 1 || H > 256 || (long long)B * K > 65535) {
+        set_last_error("pafuse_mpjpe_metrics_parts: bad argument (1 <= n_parts <= 16, B*K <= 65535, H <= 256)");
+        return PAFUSE_E_ARG;
+    }
+    for (int j = 0; j < nk; ++j)
+        if (part_of_joint[j] >= n_parts || (part_of_joint[j] >= 0 && (root_of_joint[j] < 0 || root_of_joint[j] >= nk))) {
+            set_last_error("pafuse_mpjpe_metrics_parts: joint %d has part %d / root %d out of range", j, part_of_joint[j],
+                           root_of_joint[j]);
+            return PAFUSE_E_ARG;
+        }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = sync_table(ctx->part_of_joint_host, ctx->part_of_joint_dev, part_of_joint, nk, st)) return rc;
+    if (int rc = sync_table(ctx->root_of_joint_host, ctx->root_of_joint_dev, root_of_joint, nk, st)) return rc;
+    PAFUSE_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)K * (H + 1) * n_parts * sizeof(double), st));
+    if (B == 0) return 0;
+    AggParams a;
+    a.B = B; a.K = K; a.H = H; a.F = ctx->cfg.frames; a.J = nk; a.cam_per_clip = 0;
+    a.pred = pred; a.traj = nullptr; a.cam = nullptr; a.x2d = nullptr; a.jagg = nullptr; a.pagg = nullptr; a.select = nullptr;
+    a.reproj = nullptr;
+    ProfScope ps(ctx, CAT_POST, 12.0 * a.F * a.J * ((double)B * K * H + B), st);
+    return launch_metrics_parts(a, target, ctx->part_of_joint_dev, ctx->root_of_joint_dev, n_parts, sums, st);
+}
+
+int pafuse_randn(pafuse_ctx* ctx, uint64_t seed, uint64_t draw, int64_t base, float* out, int64_t rows, int64_t row_len,
+                 int64_t row_stride, void* stream) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    if (rows == 0 || row_len == 0) return 0;
+    if (!out || rows < 0 || row_len < 0 || base < 0 || row_stride < row_len) {
+        set_last_error("pafuse_randn: bad argument (rows=%lld row_len=%lld row_stride=%lld base=%lld)", (long long)rows,
+                       (long long)row_len, (long long)row_stride, (long long)base);
+        return PAFUSE_E_ARG;
+    }
+    ProfScope ps(ctx, CAT_DDIM, 4.0 * (double)rows * row_len, (cudaStream_t)stream);
+    return launch_randn_philox(out, seed, draw, base, rows, row_len, row_stride, (cudaStream_t)stream);
+}
+
+int pafuse_set_graph_max_seqs(pafuse_ctx* ctx, int32_t max_seqs) {
+    if (!check_ctx(ctx)) return PAFUSE_E_ARG;
+    ctx->graph_max_seqs = max_seqs < 0 ? 0 : max_seqs;
+    drop_graphs(ctx);
+    return 0;
+}
+
+int64_t pafuse_graph_replays(pafuse_ctx* ctx) { return ctx ? (int64_t)ctx->graph_replays : 0; }
 
 int pafuse_prepare_clips(pafuse_ctx* ctx, const float* seq, int64_t T, float* clips, float* clips_flip, void* stream) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
@@ -851,12 +1028,14 @@ int pafuse_keypoints_from_detections(pafuse_ctx* ctx, const float* raw, int64_t 
 int pafuse_set_debug_simt_gemm(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->debug_simt = enable != 0;
+    drop_graphs(ctx);
     return 0;
 }
 
 int pafuse_set_debug_simt_attention(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->debug_simt_attn = enable != 0;
+    drop_graphs(ctx);
     ctx->ws[0].rows_x_c = 0;     // the fp32 qkv buffer exists only in debug mode: force a re-allocation
     return 0;
 }
@@ -868,24 +1047,28 @@ int pafuse_set_gemm_cta_group(int32_t cta_group) {
     }
     if (int rc = gemm_init()) return rc;
     gemm_set_cta_group(cta_group);
+    ++g_switch_epoch;
     return 0;
 }
 
 int pafuse_set_fuse_layernorm(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->fuse_ln = enable != 0;
+    drop_graphs(ctx);
     return 0;
 }
 
 int pafuse_set_fuse_mlp(pafuse_ctx* ctx, int32_t enable) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->fuse_mlp = enable != 0;
+    drop_graphs(ctx);
     return 0;
 }
 
 int pafuse_set_part_streams(pafuse_ctx* ctx, int32_t enable, const int32_t* shares) {
     if (!check_ctx(ctx)) return PAFUSE_E_ARG;
     ctx->part_streams = enable != 0;
+    drop_graphs(ctx);
     if (shares) {
         for (int pi = 0; pi < ctx->num_parts; ++pi) {
             if (shares[pi] < 2) {
@@ -902,6 +1085,7 @@ int pafuse_set_part_streams(pafuse_ctx* ctx, int32_t enable, const int32_t* shar
 int pafuse_set_gemm_weight_stationary(int32_t enable) {
     if (int rc = gemm_init()) return rc;
     gemm_set_weight_stationary(enable != 0);
+    ++g_switch_epoch;
     return 0;
 }
 

@@ -24,7 +24,7 @@ from torch import nn
 
 from . import _native
 from .h3wb import flip_permutation
-from .mixste import MixSTE2, sinusoidal_embedding_cpu, state_items
+from .mixste import MixSTE2, sinusoidal_embedding_cpu, state_items, weights_fingerprint
 
 __all__ = ["D3DP"]
 
@@ -111,8 +111,8 @@ class D3DP(nn.Module):
 
         self.noise_source = None          # optional callable(k, shape, device) -> tensor
         self.max_seqs = int(getattr(getattr(args, "b200", None), "max_seqs", 0) or 640)
-        self._natives = {}
-        self._native_dirty = True
+        self._natives = {}                # device index -> (context, fingerprint of the weights it holds)
+        self._native_dirty = False        # set to force a rebuild (e.g. after changing max_seqs)
         self._sinus_cache = {}
         self._schedule_cpu = None
 
@@ -122,24 +122,40 @@ class D3DP(nn.Module):
         (``main_h3wb.py:711-714``: keys are ``module.pose_estimator...``)."""
         if any(k.startswith("module.") for k in state_dict):
             state_dict = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
-        self._native_dirty = True
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def _apply(self, fn, *a, **k):
-        self._native_dirty = True
         self._schedule_cpu = None
         return super()._apply(fn, *a, **k)
+
+    def _replicate_for_data_parallel(self):
+        """``nn.DataParallel`` (the reference's multi-GPU mode, main_h3wb.py:699-705) re-broadcasts the weights into
+        fresh tensors for every forward; the replica carries the SOURCE module's fingerprint so that its device's
+        context is rebuilt when the source weights change, not on every forward."""
+        replica = super()._replicate_for_data_parallel()
+        replica._source_fp = self._fingerprint()
+        return replica
+
+    def _fingerprint(self):
+        fp = getattr(self, "_source_fp", None)
+        return fp if fp is not None else weights_fingerprint(self.pose_estimator)
 
     def _native(self, device) -> _native.NativeContext:
         key = torch.device(device).index
         if key is None:
             key = torch.cuda.current_device()
         if self._native_dirty:
-            for ctx in self._natives.values():
+            for ctx, _ in self._natives.values():
                 ctx.close()
             self._natives.clear()
-            self._sinus_cache.clear()
             self._native_dirty = False
+        # the packed fp16 hi/lo copies inside the library follow ANY change of the weights: load_state_dict on the
+        # module or on a child, in-place edits, .to() / .cuda() (new storage)
+        fp = self._fingerprint()
+        held = self._natives.get(key)
+        if held is not None and held[1] != fp:
+            held[0].close()
+            del self._natives[key]
         if key not in self._natives:
             parts = list(self.parts_joint_indices.items())
             ctx = _native.NativeContext(
@@ -151,8 +167,8 @@ class D3DP(nn.Module):
                 for name, t in state_items(self.pose_estimator[part]):
                     ctx.set_weight(pi, name, t)
             ctx.commit_weights()
-            self._natives[key] = ctx
-        return self._natives[key]
+            self._natives[key] = (ctx, fp)
+        return self._natives[key][0]
 
     def native_context(self, device=None):
         """The per-device C-ABI context (used by the post-processing helpers and bench)."""

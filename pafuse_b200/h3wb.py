@@ -10,6 +10,14 @@ reference prepends, ``h3wb_dataset.py:163-193``), so the tables are restated
 here as constants.  ``H3WBSkeleton`` exposes exactly the attributes the hot
 path reads from ``dataset`` (``common/diffusionpose.py:72-75``,
 ``common/utils.py:113-126``).
+
+UNVERIFIED AGAINST THE DATASET FILE: the group boundaries follow from the fixed H3WB keypoint order, but the
+left/right symmetry lists (``metadata['left_side']`` / ``['right_side']``, including the reference's duplicate
+filtering at ``h3wb_dataset.py:29-38``) live in the absent npz; the lists below are the anatomical pairs of the
+COCO-WholeBody layout and have not been compared with the file.  They only enter through ``joints_left`` /
+``joints_right``, which ``D3DP`` takes as constructor arguments: with the real dataset, pass the dataset's own lists
+(``H3WBSkeleton.from_metadata(np.load('train_h3wb.npz', allow_pickle=True)['metadata'].item())``) -- flip-TTA parity
+with a real checkpoint depends on them.
 """
 from __future__ import annotations
 
@@ -85,6 +93,26 @@ class H3WBSkeleton:
         pji["body"] = [0] + pji["body"] + pji["left_foot"] + pji["right_foot"]
         del pji["left_foot"], pji["right_foot"]
         self.parts_joint_indices = pji
+
+    @classmethod
+    def from_metadata(cls, metadata: dict, add_root: bool = True):
+        """Skeleton whose left/right side lists come from the ``metadata`` dict of ``train_h3wb.npz``
+        (``h3wb_dataset.py:26-38``, 0-based ids of the 133-keypoint layout) instead of the built-in constants; whether
+        the two agree is recorded in ``symmetry_matches_builtin`` (if not, flip-TTA pairs differ from the ones the
+        synthetic tests exercised -- the kernels take the permutation as data, so the path itself is unaffected)."""
+        sk = cls(add_root=add_root)
+        offset = 1 if add_root else 0
+        left, right = list(metadata["left_side"]), list(metadata["right_side"])
+        # h3wb_dataset.py:29-38: a joint listed on both sides is dropped from both lists
+        dups = [kp for kp in left if kp in right]
+        left = [int(e) for e in left if e not in dups]
+        right = [int(e) for e in right if e not in dups]
+        sk.symmetry_matches_builtin = (sorted(zip(left, right)) == sorted(zip(sk.metadata["left_side"], sk.metadata["right_side"])))
+        sk.metadata["left_side"], sk.metadata["right_side"] = left, right
+        sk.joints_left = [int(j) + offset for j in left]
+        sk.joints_right = [int(j) + offset for j in right]
+        sk.keypoints_metadata["keypoints_symmetry"] = [sk.joints_left, sk.joints_right]
+        return sk
 
     def kps_left(self):
         return list(self.joints_left)

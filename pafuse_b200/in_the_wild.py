@@ -16,7 +16,8 @@ from . import _native
 from .h3wb import flip_permutation
 from .utils import _post_context, eval_data_prepare, wb_pose_from_parts
 
-__all__ = ["read_openpifpaf_json", "keypoints_from_openpifpaf", "evaluate_diffusion", "stitch_predictions", "lift_video"]
+__all__ = ["read_openpifpaf_json", "keypoints_from_openpifpaf", "evaluate_diffusion", "stitch_predictions", "lift_video",
+           "save_prediction"]
 
 
 def read_openpifpaf_json(path_or_lines):
@@ -64,10 +65,28 @@ def stitch_predictions(prediction, total_frame):
     return _post_context(prediction.device, J, rf).stitch_clips(prediction, int(total_frame))
 
 
-def lift_video(model_pos, dataset, keypoints, receptive_field=27, bs=1024):
+def save_prediction(prediction, video_name, out_dir="outputs"):
+    """The reference's on-disk result (``h3wb_diffusion.py:121,136``): fp32 array ``(K,H,T,134,3)`` (camera frame,
+    before the world-frame post-processing) saved as ``<out_dir>/<video_name>/test_3d_<video_name>_output.npy``.
+    Returns the path."""
+    import os
+
+    import numpy as np
+    d = os.path.join(out_dir, video_name)
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, f"test_3d_{video_name}_output.npy")
+    np.save(path, prediction.detach().to("cpu", torch.float32).numpy(), allow_pickle=True)
+    return path
+
+
+def lift_video(model_pos, dataset, keypoints, receptive_field=27, bs=1024, video_name=None, out_dir="outputs"):
     """Whole driver: returns ``{"prediction": (K,H,T,134,3), "mean_pose": (T,134,3)}`` where ``mean_pose`` is the mean
-    over the hypotheses of the last sampling step."""
+    over the hypotheses of the last sampling step; with ``video_name`` the prediction is also written in the
+    reference's ``.npy`` format (``"path"`` in the result)."""
     T = keypoints.shape[0]
     pred = evaluate_diffusion(model_pos, dataset, keypoints, receptive_field, bs)
     out = stitch_predictions(pred, T)
-    return {"prediction": out, "mean_pose": out[-1].mean(dim=0)}
+    res = {"prediction": out, "mean_pose": out[-1].mean(dim=0)}
+    if video_name is not None:
+        res["path"] = save_prediction(out, video_name, out_dir)
+    return res

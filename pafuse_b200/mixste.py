@@ -60,9 +60,27 @@ class _SinusoidalPositionEmbeddings(nn.Module):  # keeps time_mlp indices 1 and 
 
 
 def state_items(module: nn.Module):
-    """(sub-key, tensor) pairs of one part denoiser in the C-ABI naming."""
-    for k, v in module.state_dict().items():
-        yield k, v
+    """(sub-key, tensor) pairs of one part denoiser in the C-ABI naming.  Works on ``nn.DataParallel`` replicas too:
+    their parameters are plain attributes (``_former_parameters``), which ``state_dict()`` does not list."""
+    sd = module.state_dict()
+    if sd:
+        yield from sd.items()
+        return
+    for prefix, sub in module.named_modules():
+        for k, v in getattr(sub, "_former_parameters", {}).items():
+            yield (prefix + "." if prefix else "") + k, v
+
+
+def weights_fingerprint(module: nn.Module):
+    """Cheap identity of the current weights: storage address and in-place version counter of every parameter.
+    Changes on ``load_state_dict`` of a child, ``p.data.copy_`` / init functions, optimizer steps, ``.to()``."""
+    items = []
+    for sub in module.modules():
+        for src in (sub._parameters, getattr(sub, "_former_parameters", {})):
+            for p in src.values():
+                if p is not None:
+                    items.append((p.data_ptr(), p._version))
+    return hash(tuple(items))
 
 
 class MixSTE2(nn.Module):
@@ -87,35 +105,27 @@ class MixSTE2(nn.Module):
         self.Spatial_norm = norm_layer(C)
         self.Temporal_norm = norm_layer(C)
         self.head = nn.Sequential(nn.LayerNorm(C), nn.Linear(C, 3))
-        self._natives = {}
-        self._native_dirty = True
+        self._natives = {}                # device index -> (context, fingerprint of the weights it holds)
         self.max_seqs = 640
 
-    # -- weight tracking: any (re)load or device move invalidates the packed copies
-    def load_state_dict(self, *a, **k):
-        self._native_dirty = True
-        return super().load_state_dict(*a, **k)
-
-    def _apply(self, fn, *a, **k):
-        self._native_dirty = True
-        return super()._apply(fn, *a, **k)
-
     def _native(self, device) -> _native.NativeContext:
-        key = torch.device(device).index or 0
-        if self._native_dirty:
-            for ctx in self._natives.values():
-                ctx.close()
-            self._natives.clear()
-            self._native_dirty = False
-        if key not in self._natives:
+        key = torch.device(device).index
+        if key is None:
+            key = torch.cuda.current_device()
+        fp = weights_fingerprint(self)    # the packed fp16 copies follow ANY change of the weights
+        held = self._natives.get(key)
+        if held is not None and held[1] != fp:
+            held[0].close()
+            held = None
+        if held is None:
             J = self.num_joints
             ctx = _native.NativeContext(self.num_frame, J, self.block_depth, 8, [self.embed_dim], [list(range(J))],
                                         list(range(J)), 1.0, self.max_seqs, torch.device("cuda", key))
             for name, t in state_items(self):
                 ctx.set_weight(0, name, t)
             ctx.commit_weights()
-            self._natives[key] = ctx
-        return self._natives[key]
+            held = self._natives[key] = (ctx, fp)
+        return held[0]
 
     @torch.no_grad()
     def forward(self, x_2d, x_3d, t):

@@ -147,3 +147,79 @@ def test_evaluate_metrics_is_consistent_with_aggregation():
     ep = (pagg - target[:, None]).norm(dim=-1).permute(1, 0, 2, 3).reshape(pred.shape[1], -1).double().mean(dim=-1)
     assert torch.allclose(m["J-Agg"].double(), ej, rtol=2e-6) and torch.allclose(m["P-Agg"].double(), ep, rtol=2e-6)
     assert (m["J-Best"] <= m["J-Agg"] + 1e-7).all() and (m["J-Best"] <= m["P-Best"] + 1e-7).all()
+
+
+# ------------------------------------------------------------------ part-based protocols + evaluate() accumulation
+def _golden_parts():
+    import os
+
+    import numpy as np
+    from pafuse_testlib import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "metrics_parts.npz"))
+    return {k: torch.from_numpy(g[k]) for k in g.files}
+
+
+def test_oracle_part_based_metrics_match_reference(skeleton):
+    """common/loss.py with part_based=True (values frozen by tests/golden/make_golden_metrics_parts.py)."""
+    g, gp = _golden(), _golden_parts()
+    pred, target = g["m_pred"], g["m_target"]
+    best, parts = orc.mpjpe_p_best_parts(pred, target, skeleton.parts_joint_indices, skeleton.root_indices)
+    assert torch.allclose(best, gp["p_best_pb"], rtol=1e-6, atol=0)
+    agg, agg_parts = orc.mpjpe_p_agg_parts(pred, target, skeleton.parts_joint_indices, skeleton.root_indices)
+    assert torch.allclose(agg, gp["p_agg_pb"], rtol=1e-6, atol=0)
+    for n in skeleton.parts_joint_indices:
+        assert torch.allclose(parts[n], gp[f"p_best_pb_{n}"], rtol=1e-6, atol=0)
+        assert torch.allclose(agg_parts[n], gp[f"p_agg_pb_{n}"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.gpu
+def test_part_based_metrics_kernel_against_reference_values(skeleton):
+    from pafuse_b200 import loss
+    g, gp = _golden(), _golden_parts()
+    pred, target = g["m_pred"].cuda(), g["m_target"].cuda()
+    tol = dict(rtol=2e-6, atol=0)
+    best, parts = loss.mpjpe_diffusion(pred, target, part_based=True, dataset=skeleton)
+    agg, agg_parts = loss.mpjpe_diffusion_all_min(pred, target, mean_pos=True, part_based=True, dataset=skeleton)
+    assert torch.allclose(best.cpu(), gp["p_best_pb"], **tol) and torch.allclose(agg.cpu(), gp["p_agg_pb"], **tol)
+    assert set(parts) == set(agg_parts) == {"body", "face", "left_hand", "right_hand"}
+    for n in parts:
+        assert torch.allclose(parts[n].cpu(), gp[f"p_best_pb_{n}"], **tol), n
+        assert torch.allclose(agg_parts[n].cpu(), gp[f"p_agg_pb_{n}"], **tol), n
+
+
+@pytest.mark.gpu
+def test_evaluator_reproduces_the_reference_accumulation(skeleton):
+    """Evaluator.update per sub-batch == the epoch sums / N * 1000 of evaluate() (main_h3wb.py:364-379,417-432)."""
+    from pafuse_b200 import loss
+    g, gp = _golden(), _golden_parts()
+    pred, target, t2d, rep = (g[k].cuda() for k in ("m_pred", "m_target", "m_target_2d", "m_reproj"))
+    ev = loss.Evaluator(skeleton, pred.shape[1])
+    for b in range(pred.shape[0]):
+        # J-Agg from the frozen reprojection: same path as evaluate_metrics, reproj given instead of cam + traj
+        p, t = pred[b:b + 1], target[b:b + 1]
+        m = loss._means(p, t, x2d=t2d[b:b + 1], reproj=rep[b:b + 1])
+        ev_metrics = {"J-Best": m[:, 0].float(), "P-Agg": m[:, 1].float(), "J-Agg": m[:, 2].float(),
+                      "P-Best": m[:, 3:].min(dim=1).values.float()}
+        orig = loss.evaluate_metrics
+        loss.evaluate_metrics = lambda *a, **k: ev_metrics
+        try:
+            ev.update(p, t, None, None, t2d[b:b + 1])
+        finally:
+            loss.evaluate_metrics = orig
+    res = ev.results()
+    for k in res:
+        assert torch.allclose(res[k].cpu(), gp["eval_" + k], rtol=3e-6, atol=0), k
+    lines = ev.log_lines(action="Walking")
+    assert lines[0] == "----Walking----" and lines[-1] == "----------"
+    assert lines[1] == "step 0 : Protocol #1 Error (MPJPE) J_Best: %f mm" % res["J_Best"][0].item()
+    assert sum("Part-Based HANDS" in l for l in lines) == 2 * pred.shape[1]
+
+
+@pytest.mark.gpu
+def test_metrics_of_an_empty_batch_are_nan_not_a_crash(skeleton):
+    from pafuse_b200 import loss
+    pred = torch.zeros(0, 2, 3, 27, 134, 3, device="cuda")
+    target = torch.zeros(0, 27, 134, 3, device="cuda")
+    assert torch.isnan(loss.mpjpe_diffusion_all_min(pred, target)).all()
+    best, parts = loss.mpjpe_diffusion(pred, target, part_based=True, dataset=skeleton)
+    assert torch.isnan(best).all() and set(parts) == {"body", "face", "left_hand", "right_hand"}

@@ -1,6 +1,15 @@
-"""Per-kernel, per-part summary of an ncu --csv launch list (time, DRAM bytes, tensor-pipe %).
+"""Per-kernel, per-part summary of an ncu --csv launch list (time, DRAM bytes, tensor-pipe activity).
 
+    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,\
+sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,\
+sm__ops_path_tensor_op_hmma_src_fp16_dst_fp32_realtime.sum,sm__inst_executed_pipe_tensor_subpipe_hmma.sum \
+        --clock-control none --csv --log-file gpurun_out/x_launches.csv python tools/profile_pass.py 640
     python tools/ncu_by_part.py gpurun_out/x_launches.csv
+
+Tensor-pipe columns: tcgen05 kernels do NOT populate sm__pipe_tensor_subpipe_hmma_cycles_active_realtime (the round-1
+lists showed 0.0); on gb100 UTCHMMA work is visible as sm__pipe_tensor_cycles_active_realtime (cycles the pipe was
+busy, % of elapsed) and as sm__ops_path_tensor_op_hmma_src_fp16_dst_fp32_realtime (math ops executed: / time = the
+tensor TFLOP/s actually issued, all three f16x3 passes and the padding included).
 """
 import collections
 import csv
@@ -34,20 +43,23 @@ def main(path):
     for d in L.values():
         if d['k'].startswith('embed'):
             part += 1
-        a = agg.setdefault((part, d['k']), [0, 0.0, 0.0, 0.0, 0.0])
+        a = agg.setdefault((part, d['k']), [0, 0.0, 0.0, 0.0, 0.0, 0.0])
         a[0] += 1
         a[1] += d.get('gpu__time_duration.sum', 0.0)
         a[2] += d.get('dram__bytes_read.sum', 0.0)
         a[3] += d.get('dram__bytes_write.sum', 0.0)
-        a[4] += d.get('sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 0.0)
+        a[4] += max(d.get('sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 0.0),
+                    d.get('sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 0.0))
+        a[5] += d.get('sm__ops_path_tensor_op_hmma_src_fp16_dst_fp32_realtime.sum', 0.0)
     tot = sum(a[1] for a in agg.values())
     print(f"# {path}: {len(L)} launches, {tot / 1e3:.2f} ms summed (cold-cache, serialised under ncu)")
-    print(f"{'part':6s}{'kernel':40s}{'n':>4s}{'avg us':>9s}{'share':>7s}{'rd MB':>9s}{'wr MB':>9s}{'DRAM GB/s':>10s}{'tensor %':>9s}")
+    print(f"{'part':6s}{'kernel':40s}{'n':>4s}{'avg us':>9s}{'share':>7s}{'rd MB':>9s}{'wr MB':>9s}{'DRAM GB/s':>10s}{'tensor %':>9s}"
+          f"{'issued TF/s':>12s}")
     for (p, n), a in agg.items():
         nm = names[p % 3] if p >= 0 else '-'
         us = a[1] / a[0]
         print(f"{nm:6s}{n:40s}{a[0]:4d}{us:9.1f}{100 * a[1] / tot:6.1f}%{a[2] / a[0] / 1e6:9.1f}{a[3] / a[0] / 1e6:9.1f}"
-              f"{(a[2] + a[3]) / a[1] / 1e3:10.0f}{a[4] / a[0]:9.1f}")
+              f"{(a[2] + a[3]) / a[1] / 1e3:10.0f}{a[4] / a[0]:9.1f}{a[5] / a[1] / 1e6 if a[1] else 0.0:12.1f}")
 
 
 if __name__ == '__main__':
