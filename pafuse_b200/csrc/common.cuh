@@ -113,6 +113,8 @@ __device__ __forceinline__ void split_op(float v, op_t& hi, op_t& lo) {
     hi = __float2half_rn(v);
     lo = __float2half_rn(v - __half2float(hi));
 }
+// torch.clamp semantics: a NaN stays a NaN (fminf / fmaxf alone would return the bound)
+__device__ __forceinline__ float clamp_keep_nan(float v, float lo, float hi) { return v != v ? v : fminf(fmaxf(v, lo), hi); }
 __device__ __forceinline__ float join_op(op_t hi, op_t lo) { return __half2float(hi) + __half2float(lo); }
 
 __device__ __forceinline__ uint32_t pack_op2(op_t a, op_t b) {

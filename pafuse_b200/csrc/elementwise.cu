@@ -118,7 +118,7 @@ __global__ void embed_kernel(EmbedParams p) {
     for (int c = 0; c < 3; ++c) {
         float v = x3[c];
         if (p.apply_clamp) {
-            v = fminf(fmaxf(v, -p.clamp), p.clamp);
+            v = clamp_keep_nan(v, -p.clamp, p.clamp);
             v = __fdiv_rn(v, p.scale);
         }
         in[2 + c] = v;
@@ -372,7 +372,7 @@ __global__ void ddim_step_kernel(DdimParams p) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float x0 = __fmul_rn(x0v[c], p.scale);
-        x0 = fminf(fmaxf(x0, -p.clamp), p.clamp);
+        x0 = clamp_keep_nan(x0, -p.clamp, p.clamp);
         x0o[c] = x0;
         if (p.last) {
             img[c] = x0;
@@ -456,8 +456,8 @@ int launch_negate_rows(float* x, const int* rows, int nrows, long long poses, in
 // ------------------------------------------------------------------ projection + aggregation
 // camera.py:30-60 restated with the same operation order (all roundings explicit).
 __device__ __forceinline__ void project_point(const float X[3], const float* __restrict__ cam, float uv[2]) {
-    float xx0 = fminf(fmaxf(__fdiv_rn(X[0], X[2]), -1.f), 1.f);
-    float xx1 = fminf(fmaxf(__fdiv_rn(X[1], X[2]), -1.f), 1.f);
+    float xx0 = clamp_keep_nan(__fdiv_rn(X[0], X[2]), -1.f, 1.f);
+    float xx1 = clamp_keep_nan(__fdiv_rn(X[1], X[2]), -1.f, 1.f);
     float r2 = __fadd_rn(__fmul_rn(xx0, xx0), __fmul_rn(xx1, xx1));
     float r4 = __fmul_rn(r2, r2);
     float r6 = __fmul_rn(r4, r2);

@@ -77,9 +77,9 @@ def mpjpe_diffusion_all_min(predicted, target, mean_pos=False, part_based=False,
     if not mean_pos:
         raise NotImplementedError("mpjpe_diffusion_all_min(part_based=True, mean_pos=False) is not called by evaluate()")
     B, K, H, F, J, _ = predicted.shape
-    names, counts, sums = _part_means(predicted, target, dataset)
     if B == 0:
-        return _empty(K, predicted.device), {n: _empty(K, predicted.device) for n in names}
+        return _empty(K, predicted.device), {n: _empty(K, predicted.device) for n in dataset.parts_joint_indices}
+    names, counts, sums = _part_means(predicted, target, dataset)
     row = sums[:, H, :]                                        # (K, n_parts) sums of |mean_h pc - gc|
     errors = (row.sum(dim=1) / float(B * F * J)).float()       # joints outside every part contribute 0, like zeros_like
     parts = {n: (row[:, i] / (float(B * F) * counts[i])).float() for i, n in enumerate(names)}
@@ -97,9 +97,9 @@ def mpjpe_diffusion(predicted, target, mean_pos=False, part_based=False, dataset
         m = _means(predicted, target)
         return m[:, 3:].min(dim=1).values.float(), {}
     B, K, H, F, J, _ = predicted.shape
-    names, counts, sums = _part_means(predicted, target, dataset)
     if B == 0:
-        return _empty(K, predicted.device), {n: _empty(K, predicted.device) for n in names}
+        return _empty(K, predicted.device), {n: _empty(K, predicted.device) for n in dataset.parts_joint_indices}
+    names, counts, sums = _part_means(predicted, target, dataset)
     per_h = sums[:, :H, :]                                     # (K, H, n_parts)
     total = (per_h.sum(dim=2) / float(B * F * J)).float()      # (K, H) fp32 like the reference's means, so ties break alike
     min_errors, min_inds = total.min(dim=1)
