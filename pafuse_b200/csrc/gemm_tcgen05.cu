@@ -17,13 +17,20 @@
 //   warp 0    TMA producer: 4 tiled loads per stage (A_hi, A_lo, W_hi, W_lo; 128B swizzle)
 //   warp 1    MMA issuer (even CTA only): 3 x (BK/16) tcgen05.mma per stage, commits to mbarriers
 //   warp 2    TMEM allocator (512 columns = two BN<=256 accumulator buffers)
-//   warps 4-11 epilogue, two warps per TMEM lane quarter (even / odd 32-column chunks): tcgen05.ld 32 lanes
-//             x 32 columns, bias / GELU+split, swizzled st.shared into a per-warp staging box, TMA store of
-//             the box (cp.reduce.async.bulk .add for the residual update x += y, performed at the L2).
-//             The first version stored straight from registers, one row per lane: 32 different 128-byte
-//             lines per store instruction made the epilogue the critical path (profiles/r1a_*); the second
-//             had 4 epilogue warps and the GELU / head-plane epilogues (40 instructions per element at
-//             0.4 IPC) were still slower than the main loop (profiles/r1b_gemm_attention_ncu_full.txt).
+//   warps 4-19 epilogue, FOUR warps per TMEM lane quarter, each taking every fourth 16-column chunk: tcgen05.ld
+//             32 lanes x 16 columns, bias / GELU+split / residual + LayerNorm, swizzled st.shared into a per-warp
+//             2 KB staging box, TMA store of the box (cp.reduce.async.bulk .add for the residual update x += y,
+//             performed at the L2).  Registers: setmaxnreg moves the control warpgroup down to REGS_CTRL and the four
+//             epilogue warpgroups up to REGS_EPI.
+//             History: v1 stored straight from registers, one row per lane: 32 different 128-byte lines per store
+//             instruction made the epilogue the critical path (profiles/r1a_*); v2 had 4 epilogue warps and the
+//             GELU / head-plane epilogues (40 instructions per element at 0.4 IPC) were still slower than the main
+//             loop (profiles/r1b_gemm_attention_ncu_full.txt); v3 (round 1) had 8 warps on 32-column chunks: every
+//             epilogue is a serial chain tcgen05.ld -> math -> st.shared -> TMA store per chunk, and with two warps
+//             per scheduler those chains ran at IPC ~0.2 and paced the face / hands launches (fc1 and qkv issue
+//             bound, proj / fc2 at 5 TB/s, profiles/r1n_epilogue_analysis.txt).  Sixteen warps give every scheduler
+//             four independent chains; 16-column chunks keep the staging at 32 KB and the per-thread state small
+//             enough for 640 threads.
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue),
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "kernels.cuh"
@@ -41,14 +48,21 @@ constexpr int BKW = 64;              // K extent of a W box = one 128-byte swizz
 constexpr int UK = 16;               // K per tcgen05.mma (16-bit operands)
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int SMEM_SLACK = 1024 + 512;              // alignment of the dynamic window + the static barriers
-constexpr int SMEM_SLACK_LN = 1024 + 512 + 1024;    // + the row-sum exchange buffer of EPI_RESID_LN
-constexpr int NUM_THREADS = 384;
+// static shared memory (barriers; + the 2 KB statistics exchange buffer of EPI_RESID_LN) rounded up to the 1024-byte
+// alignment of the dynamic window that follows it
+constexpr int SMEM_SLACK = 1024;
+constexpr int SMEM_SLACK_LN = 3072;
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_SUBS = EPI_WARPS / 4;             // epilogue warps per TMEM lane quarter
+constexpr int NUM_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // 640
+constexpr int CW = 16;                              // accumulator columns per epilogue chunk
 constexpr int TMEM_COLS = 512;
-constexpr int STG_WARP_BYTES = 4096;                // per epilogue warp: one staging box of 32 rows x 128 B
+constexpr int STG_WARP_BYTES = 2048;                // per epilogue warp: one staging box of 32 rows x 64 B (fp32) or hi + lo boxes of 32 rows x 32 B
 constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
+// register budget (setmaxnreg, per thread): 4 control warps x 32 x 64 + 16 epilogue warps x 32 x 104 = 61440 <= 65536
+#define PAFUSE_REGS_CTRL "64"
+#define PAFUSE_REGS_EPI "104"
 
 struct KernelParams {
     long long M;
@@ -62,8 +76,7 @@ struct KernelParams {
     int slots;                       // weight-stationary mode: groups of n_tiles CTA pairs
     float out_scale;                 // undoes WEIGHT_SCALE
     const float* bias;
-    int hds;                         // EPI_PLANES: stored head width (columns per plane)
-    int plane_pw;                    // EPI_PLANES: columns per output box, 32 (hds % 32 == 0) or 16
+    int hds;                         // EPI_PLANES: stored head width (columns per plane, a multiple of 16)
     GemmLnFuse ln;                   // EPI_RESID_LN
 };
 
@@ -102,19 +115,51 @@ struct TileWalk {
     }
 };
 
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t r[32]) {
+// 32 lanes x 16 consecutive 32-bit columns <-> 16 registers per thread (thread i <-> lane base + i)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t r[16]) {
     asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t r[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t r[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait_all() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+// the EPI_SUBS warps that share a TMEM lane quarter (128 threads), barrier id 1 + quarter
+__device__ __forceinline__ void quarter_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+// staging-box offsets of 16-byte piece i of row `row`: fp32 boxes are 32 rows x 64 B with the 64-byte swizzle
+// (piece i at i ^ ((row >> 1) & 3)), fp16 boxes 32 rows x 32 B with the 32-byte swizzle (piece i at i ^ ((row >> 2) & 1));
+// both patterns are bank-conflict free for a quarter-warp of consecutive rows
+__device__ __forceinline__ uint32_t box_off_f32(int row, int i) { return (uint32_t)(row * 64 + ((i ^ ((row >> 1) & 3)) << 4)); }
+__device__ __forceinline__ uint32_t box_off_f16(int row, int i) { return (uint32_t)(row * 32 + ((i ^ ((row >> 2) & 1)) << 4)); }
+// 16 values -> fp16 hi / lo boxes (hi at +0, lo at +1024) of this warp's staging area
+__device__ __forceinline__ void stage_split16(uint32_t box_s, int lane, const float (&v)[16]) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_pair_sat(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const uint32_t off = box_off_f16(lane, i);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box_s + off), "r"(hi[4 * i]), "r"(hi[4 * i + 1]),
+                     "r"(hi[4 * i + 2]), "r"(hi[4 * i + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box_s + 1024 + off), "r"(lo[4 * i]), "r"(lo[4 * i + 1]),
+                     "r"(lo[4 * i + 2]), "r"(lo[4 * i + 3]) : "memory");
+    }
+}
 
 // Epilogue of the residual GEMMs (proj, fc2) of the parts whose rows fit one tile (N == BN <= 256), fused with the
 // LayerNorms that follow them (mixste.py:114-115 norm2; :243,257,269,273 the shared norm that closes the block,
@@ -123,17 +168,17 @@ __device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %
 //     not chained:  x <- v ;                          a = LN(v; g1, b1)   -> fp16 hi/lo
 //     chained:      x <- y = LN(v; g0, b0) [+ add_f[f]] ;  a = LN(y; g1, b1)   -> fp16 hi/lo
 // It replaces the L2-side reduction of EPI_RESID plus one ln_chain_kernel launch (8-12 B per element of DRAM
-// traffic).  A thread owns one row (= TMEM lane); the two warps of a lane quarter split the 32-column chunks
-// (even / odd) and exchange their partial row sums through shared memory.  The row values stay in the
-// accumulator's tensor memory between the passes (tcgen05.st / tcgen05.ld); statistics are gathered in the pass
-// that produces the values (shifted sums, see merge_stats).  x is fetched with coalesced 16-byte loads one chunk ahead (registers), transposed through the
-// warp's staging box, which then carries the output row by row to the TMA store.
-// coalesced fetch of a 32 x 32 box of x: lane -> 16 bytes at column (lane & 7) * 4 of rows (lane >> 3) + 4 i
-__device__ __forceinline__ void ln_fetch_x(const KernelParams& p, float4 (&xr)[8], int row0, int c0, int lane) {
+// traffic).  A thread owns one row (= TMEM lane); the EPI_SUBS warps of a lane quarter take every EPI_SUBS-th 16-column
+// chunk and merge their partial row statistics through shared memory (one exchange per norm).  The row values stay in
+// the accumulator's tensor memory between the passes (tcgen05.st / tcgen05.ld); statistics are gathered in the pass that
+// produces the values (shifted sums, see merge_stats).  x is fetched with coalesced 16-byte loads one chunk ahead
+// (registers), transposed through the warp's staging box, which then carries the output row by row to the TMA store.
+// coalesced fetch of a 32 x 16 box of x: lane -> 16 bytes at column (lane & 3) * 4 of rows (lane >> 2) + 8 i
+__device__ __forceinline__ void ln_fetch_x(const KernelParams& p, float4 (&xr)[4], int row0, int c0, int lane) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const long long r = (long long)row0 + (lane >> 3) + 4 * i;
-        xr[i] = r < p.M ? __ldg(reinterpret_cast<const float4*>(p.ln.x + (size_t)r * p.N + c0 + (lane & 7) * 4))
+    for (int i = 0; i < 4; ++i) {
+        const long long r = (long long)row0 + (lane >> 2) + 8 * i;
+        xr[i] = r < p.M ? __ldg(reinterpret_cast<const float4*>(p.ln.x + (size_t)r * p.N + c0 + (lane & 3) * 4))
                         : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
@@ -141,21 +186,18 @@ __device__ __forceinline__ void ln_fetch_x(const KernelParams& p, float4 (&xr)[8
 __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-__device__ __forceinline__ void sts128u(uint32_t addr, const uint4& v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
-// 32 consecutive floats of a per-column parameter vector, the same for every lane (broadcast loads).  Issued as one
+// 16 consecutive floats of a per-column parameter vector, the same for every lane (broadcast loads).  Issued as one
 // batch ahead of their use: loaded one by one next to the FMAs they feed, every load's latency was exposed
 // (profiles/r1j_*: a quarter of the epilogue time).
-__device__ __forceinline__ void load_vec32(float4 (&v)[8], const float* src) {
+__device__ __forceinline__ void load_vec16(float4 (&v)[4], const float* src) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __ldg(s4 + i);
+    for (int i = 0; i < 4; ++i) v[i] = __ldg(s4 + i);
 }
 
 // (A bulk L2 prefetch of the next tile's residual rows -- they are one contiguous range of x -- was tried against the
@@ -163,100 +205,71 @@ __device__ __forceinline__ void load_vec32(float4 (&v)[8], const float* src) {
 template <int CG>
 __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const CUtensorMap& tm_x, const CUtensorMap& tm_hi,
                                                   const CUtensorMap& tm_lo, uint8_t* box, float* xch, uint32_t t_base,
-                                                  int row0, int q, int half, int lane, int BN, float oscale,
-                                                  uint64_t* tmem_empty, float4 (&xr)[8]) {
+                                                  int row0, int q, int sub, int lane, int BN, float oscale,
+                                                  uint64_t* tmem_empty, float4 (&xr)[4]) {
     const GemmLnFuse& f = p.ln;
     const int N = p.N;
-    const int nchunks = (BN / 32 - half + 1) / 2;                     // chunks half, half + 2, ...
+    const int nck = BN / CW;
+    const int mine = (nck - sub + EPI_SUBS - 1) / EPI_SUBS;           // chunks sub, sub + EPI_SUBS, ... (may be 0)
     const bool chained = f.g0 != nullptr;
     const float invN = 1.0f / (float)N;
-    float* my_x = xch + (q * 32 + lane) * 2;
+    float* my_x = xch + (q * 32 + lane) * EPI_SUBS;
     const int bar_id = 1 + q;
     const uint32_t box_s = smem_u32(box);
-    const uint32_t row_s = box_s + lane * 128;                        // this lane's row of a 32 x 128 B box
-    const int sw = lane & 7;
 
-    auto partner = [&](float v) -> float {                            // value of the warp that shares this row
-        my_x[half] = v;
-        pair_bar_sync(bar_id);
-        const float o = my_x[half ^ 1];
-        pair_bar_sync(bar_id);                                        // the slot may be rewritten after this point
-        return o;
-    };
     // Row statistics in ONE pass over the values (a second tensor-memory pass per norm cost 40 % of the epilogue):
     // each warp accumulates S = sum(v - K), Q = sum((v - K)^2) around K = its first value of the row, which keeps
-    // Q - S^2/n free of cancellation; the two warps' (mean, M2) are merged with the pairwise update of Chan et al.
-    const float na = (float)(nchunks * 32), nb = (float)N - na;
-    auto merge_stats = [&](float K, float S, float Q, float eps, float& mean, float& rstd) {
-        const float mean_a = na > 0.f ? K + S / na : 0.f;               // a 32-column row leaves the odd warp empty
-        const float m2_a = na > 0.f ? Q - S * S / na : 0.f;
-        const float mean_b = partner(mean_a);
-        const float m2_b = partner(m2_a);
-        const float delta = mean_b - mean_a;
-        mean = mean_a + delta * (nb * invN);
-        const float m2 = m2_a + m2_b + delta * delta * (na * nb * invN);
-        rstd = 1.0f / sqrtf(m2 * invN + eps);
+    // Q - S^2/n free of cancellation; the warps' (mean, M2) are merged with the pairwise update of Chan et al., by
+    // every warp in the same order, so all of them hold bit-identical statistics.
+    // The exchange buffer holds ONE float per (row, warp) -- 2 KB, which is what the operand ring leaves at C = 256 --
+    // so means and M2s travel in two rounds.
+    auto exchange = [&](float mine_v, float (&all)[EPI_SUBS]) {
+        my_x[sub] = mine_v;
+        quarter_bar_sync(bar_id);
+#pragma unroll
+        for (int s = 0; s < EPI_SUBS; ++s) all[s] = my_x[s];
+        quarter_bar_sync(bar_id);                                     // the slots may be rewritten after this point
     };
-    // LN(v; g, b) of the row values held in tensor memory -> fp16 hi/lo boxes -> TMA stores
-    auto emit_split = [&](float mean, float rstd, const float* g, const float* b) {
-        const float mr = -mean * rstd;
-        for (int ci = 0; ci < nchunks; ++ci) {
-            const int c0 = (half + 2 * ci) * 32;
-            uint32_t r[32];
-            float4 gv[8], bv[8];
-            tmem_ld_32x32(t_base + (uint32_t)c0, r);
-            load_vec32(gv, g + c0);
-            load_vec32(bv, b + c0);
-            tmem_ld_wait();
-            uint32_t hi[16], lo[16];
+    auto merge_stats = [&](float K, float S, float Q, float eps, float& mean, float& rstd) {
+        const float na = (float)(mine * CW);
+        float means[EPI_SUBS], m2s[EPI_SUBS];
+        exchange(mine > 0 ? K + S / na : 0.f, means);
+        exchange(mine > 0 ? Q - S * S / na : 0.f, m2s);
+        float n_acc = 0.f, mean_acc = 0.f, m2_acc = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float v0 = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), rstd, mr), gv[i].x, bv[i].x);
-                const float v1 = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), rstd, mr), gv[i].y, bv[i].y);
-                const float v2 = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), rstd, mr), gv[i].z, bv[i].z);
-                const float v3 = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), rstd, mr), gv[i].w, bv[i].w);
-                split_pair_sat(v0, v1, hi[2 * i], lo[2 * i]);
-                split_pair_sat(v2, v3, hi[2 * i + 1], lo[2 * i + 1]);
-            }
-            if (lane == 0) bulk_wait_group_read<0>();                 // the store that last used the box has read it
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t off = (uint32_t)(lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4));   // 32 rows x 64 B, 64-byte swizzle
-                sts128u(box_s + off, make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]));
-                sts128u(box_s + 2048 + off, make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]));
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_2d(&tm_hi, box, c0, row0);
-                tma_store_2d(&tm_lo, box + 2048, c0, row0);
-                bulk_commit_group();
+        for (int s = 0; s < EPI_SUBS; ++s) {
+            const int cnt = (nck - s + EPI_SUBS - 1) / EPI_SUBS;
+            if (cnt > 0) {                                            // warp-uniform
+                const float n_s = (float)(cnt * CW), n_new = n_acc + n_s;
+                const float delta = means[s] - mean_acc;
+                mean_acc += delta * (n_s / n_new);
+                m2_acc += m2s[s] + delta * delta * (n_acc * n_s / n_new);
+                n_acc = n_new;
             }
         }
+        mean = mean_acc;
+        rstd = 1.0f / sqrtf(m2_acc * invN + eps);
     };
 
     // ---- pass 1: v = x + acc * scale + bias -> tensor memory (and, when not chained, -> x)
     float K = 0.f, S = 0.f, Q = 0.f;
-    for (int ci = 0; ci < nchunks; ++ci) {
-        const int c0 = (half + 2 * ci) * 32;
-        uint32_t r[32];
-        float4 bv[8];
-        tmem_ld_32x32(t_base + (uint32_t)c0, r);
-        load_vec32(bv, p.bias + c0);
+    for (int ci = 0; ci < mine; ++ci) {
+        const int c0 = (sub + EPI_SUBS * ci) * CW;
+        uint32_t r[16];
+        float4 bv[4];
+        tmem_ld_32x16(t_base + (uint32_t)c0, r);
+        load_vec16(bv, p.bias + c0);
         if (lane == 0) bulk_wait_group_read<0>();                     // the store that last used the box has read it
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {                                 // transpose x through the box (128-byte swizzle)
-            const int rr = (lane >> 3) + 4 * i;
-            sts128(box_s + (uint32_t)(rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)), xr[i]);
-        }
+        for (int i = 0; i < 4; ++i)                                   // transpose x through the box
+            sts128(box_s + box_off_f32((lane >> 2) + 8 * i, lane & 3), xr[i]);
         __syncwarp();
-        if (ci + 1 < nchunks) ln_fetch_x(p, xr, row0, c0 + 64, lane);  // next chunk's x, in flight during the math
+        if (ci + 1 < mine) ln_fetch_x(p, xr, row0, c0 + EPI_SUBS * CW, lane);   // next chunk's x, in flight during the math
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t slot = row_s + (uint32_t)((i ^ sw) << 4);
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t slot = box_s + box_off_f32(lane, i);
             const float4 xv = lds128(slot);
             float4 v;
             v.x = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bv[i].x) + xv.x;
@@ -275,7 +288,7 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
             r[4 * i + 3] = __float_as_uint(v.w);
             if (!chained) sts128(slot, v);
         }
-        tmem_st_32x32(t_base + (uint32_t)c0, r);
+        tmem_st_32x16(t_base + (uint32_t)c0, r);
         if (!chained) {
             fence_proxy_async_smem();
             __syncwarp();
@@ -295,49 +308,44 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         const long long row = (long long)row0 + lane;
         const float* addr = f.add_f ? f.add_f + (size_t)((row / f.J) % f.F) * N : nullptr;
         K = 0.f; S = 0.f; Q = 0.f;
-        for (int ci = 0; ci < nchunks; ++ci) {
-            const int c0 = (half + 2 * ci) * 32;
-            uint32_t r[32];
-            float4 gv[8], bv[8];
-            tmem_ld_32x32(t_base + (uint32_t)c0, r);
-            load_vec32(gv, f.g0 + c0);
-            load_vec32(bv, f.b0 + c0);
+        for (int ci = 0; ci < mine; ++ci) {
+            const int c0 = (sub + EPI_SUBS * ci) * CW;
+            uint32_t r[16];
+            float4 gv[4], bv[4];
+            tmem_ld_32x16(t_base + (uint32_t)c0, r);
+            load_vec16(gv, f.g0 + c0);
+            load_vec16(bv, f.b0 + c0);
             tmem_ld_wait();
+            float4 y[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 y;
-                y.x = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), rstd, mr), gv[i].x, bv[i].x);
-                y.y = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), rstd, mr), gv[i].y, bv[i].y);
-                y.z = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), rstd, mr), gv[i].z, bv[i].z);
-                y.w = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), rstd, mr), gv[i].w, bv[i].w);
-                r[4 * i + 0] = __float_as_uint(y.x);
-                r[4 * i + 1] = __float_as_uint(y.y);
-                r[4 * i + 2] = __float_as_uint(y.z);
-                r[4 * i + 3] = __float_as_uint(y.w);
+            for (int i = 0; i < 4; ++i) {
+                y[i].x = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), rstd, mr), gv[i].x, bv[i].x);
+                y[i].y = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), rstd, mr), gv[i].y, bv[i].y);
+                y[i].z = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), rstd, mr), gv[i].z, bv[i].z);
+                y[i].w = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), rstd, mr), gv[i].w, bv[i].w);
             }
             if (addr) {                                               // Temporal_pos_embed (after STE block 0 only)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     const float4 a = __ldg(reinterpret_cast<const float4*>(addr + c0) + i);
-                    r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + a.x);
-                    r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + a.y);
-                    r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + a.z);
-                    r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + a.w);
+                    y[i].x += a.x; y[i].y += a.y; y[i].z += a.z; y[i].w += a.w;
                 }
             }
             if (lane == 0) bulk_wait_group_read<0>();
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 y = make_float4(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]),
-                                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                if (ci == 0 && i == 0) K = y.x;
-                const float d0 = y.x - K, d1 = y.y - K, d2 = y.z - K, d3 = y.w - K;
+            for (int i = 0; i < 4; ++i) {
+                if (ci == 0 && i == 0) K = y[i].x;
+                const float d0 = y[i].x - K, d1 = y[i].y - K, d2 = y[i].z - K, d3 = y[i].w - K;
                 S += (d0 + d1) + (d2 + d3);
                 Q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, Q))));
-                sts128(row_s + (uint32_t)((i ^ sw) << 4), y);
+                sts128(box_s + box_off_f32(lane, i), y[i]);
+                r[4 * i + 0] = __float_as_uint(y[i].x);
+                r[4 * i + 1] = __float_as_uint(y[i].y);
+                r[4 * i + 2] = __float_as_uint(y[i].z);
+                r[4 * i + 3] = __float_as_uint(y[i].w);
             }
-            tmem_st_32x32(t_base + (uint32_t)c0, r);
+            tmem_st_32x16(t_base + (uint32_t)c0, r);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -348,7 +356,38 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         tmem_st_wait_all();
         merge_stats(K, S, Q, f.eps1, mean, rstd);
     }
-    emit_split(mean, rstd, f.g1, f.b1);
+
+    // ---- a = LN(row values in tensor memory; g1, b1) -> fp16 hi/lo boxes -> TMA stores
+    {
+        const float mr = -mean * rstd;
+        for (int ci = 0; ci < mine; ++ci) {
+            const int c0 = (sub + EPI_SUBS * ci) * CW;
+            uint32_t r[16];
+            float4 gv[4], bv[4];
+            tmem_ld_32x16(t_base + (uint32_t)c0, r);
+            load_vec16(gv, f.g1 + c0);
+            load_vec16(bv, f.b1 + c0);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                v[4 * i + 0] = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), rstd, mr), gv[i].x, bv[i].x);
+                v[4 * i + 1] = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), rstd, mr), gv[i].y, bv[i].y);
+                v[4 * i + 2] = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), rstd, mr), gv[i].z, bv[i].z);
+                v[4 * i + 3] = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), rstd, mr), gv[i].w, bv[i].w);
+            }
+            if (lane == 0) bulk_wait_group_read<0>();                 // the store that last used the box has read it
+            __syncwarp();
+            stage_split16(box_s, lane, v);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(&tm_hi, box, c0, row0);
+                tma_store_2d(&tm_lo, box + 1024, c0, row0);
+                bulk_commit_group();
+            }
+        }
+    }
 
     // the accumulator buffer goes back to the MMA issuer
     tcgen05_fence_before();
@@ -365,8 +404,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                   const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                   const __grid_constant__ CUtensorMap tm_out0, const __grid_constant__ CUtensorMap tm_out1,
                   const __grid_constant__ CUtensorMap tm_out2, const KernelParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ float ln_xch[EPI == EPI_RESID_LN ? 128 * 2 : 2];   // partial row sums of the two warps that share a row
+    extern __shared__ __align__(1024) uint8_t smem_raw[];           // the operand tiles need 1024-byte boundaries (128B swizzle atoms)
+    __shared__ float ln_xch[EPI == EPI_RESID_LN ? 128 * EPI_SUBS : 1];   // partial row statistics of the warps that share a row
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
@@ -374,8 +413,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     __shared__ __align__(8) uint64_t w_full_bar;
     __shared__ uint32_t tmem_base_slot;
 
-    // operand tiles must sit on 1024-byte boundaries for the 128B swizzle atoms
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw;
     uint8_t* smem_w = smem;                                   // WRES: [K/64][hi, lo][WN rows x 128 B]
     uint8_t* smem_st = smem + (WRES ? p.w_res_bytes : 0);     // operand stage ring
     uint8_t* smem_box = smem_st + (size_t)p.stages * p.stage_bytes;
@@ -394,6 +432,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
+        if (smem_u32(smem_raw) & 1023u) {                             // the launch code sizes the ring for an aligned window
+            printf("pafuse: dynamic shared memory is not 1024-byte aligned\n");
+            asm volatile("trap;");
+        }
         prefetch_tensormap(&tm_a_hi);
         prefetch_tensormap(&tm_a_lo);
         prefetch_tensormap(&tm_w_hi);
@@ -426,6 +468,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     // fetches its W slice (weights are not written by any kernel of the chain) before it joins the wait
     if (!(WRES && warp == 0)) pdl_wait();
 
+    if (warp < EPI_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 " PAFUSE_REGS_CTRL ";");   // the control warpgroup donates registers ...
     if (warp == 0) {
         // ===================== TMA producer (every CTA loads its own operands) =====================
         if (WRES) {
@@ -539,69 +583,69 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 if (acc == 0) acc_phase ^= 1;
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " PAFUSE_REGS_EPI ";");   // ... to the four epilogue warpgroups
         // ===================== epilogue (every CTA drains its own 128 accumulator rows) =====================
         const int q = warp & 3;                                       // TMEM lane quarter == warp % 4
-        const int half = (warp - EPI_WARP0) >> 2;                     // 0: even 32-column chunks, 1: odd
+        const int sub = (warp - EPI_WARP0) >> 2;                      // takes the 16-column chunks sub, sub + EPI_SUBS, ...
+        const int nck = BN / CW;
         int acc = 0;
         uint32_t acc_phase = 0;
         const float oscale = p.out_scale;
         uint8_t* box = smem_box + (warp - EPI_WARP0) * STG_WARP_BYTES;   // 1024-byte aligned
+        const uint32_t box_s = smem_u32(box);
+        auto release = [&](uint64_t* bar) {                           // this warp's share of the accumulator is read
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {                                          // EPI_WARPS*CG arrivals release the buffer to the issuer
+                if (CG == 1) mbar_arrive(bar);
+                else mbar_arrive_cluster(bar, 0);
+            }
+        };
         for (int it = 0; it < walk.count; ++it) {
             int m_tile, n_tile;
             walk.at(it, m_tile, n_tile);
             const int row0 = (m_tile * CG + (int)cta_rank) * BM + q * 32;   // first row of this warp's box
-            float4 xr[8];                                             // EPI_RESID_LN: x of the next chunk
+            float4 xr[4];                                             // EPI_RESID_LN: x of the next chunk
             if (EPI == EPI_RESID_LN) {
-                ln_fetch_x(p, xr, row0, half * 32, lane);             // in flight while the main loop finishes
+                if (sub < nck) ln_fetch_x(p, xr, row0, sub * CW, lane);   // in flight while the main loop finishes
             }
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
             if (EPI == EPI_RESID_LN) {
-                epilogue_resid_ln<CG>(p, tm_out0, tm_out1, tm_out2, box, ln_xch, t_base, row0, q, half, lane, BN, oscale,
+                epilogue_resid_ln<CG>(p, tm_out0, tm_out1, tm_out2, box, ln_xch, t_base, row0, q, sub, lane, BN, oscale,
                                       &tmem_empty_bar[acc], xr);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
                 continue;
             }
-            if (half * 32 >= BN) {                                    // a 32-column tile has no odd chunk: nothing to read
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 1) mbar_arrive(&tmem_empty_bar[acc]);
-                    else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-                }
-            }
-            for (int c0 = half * 32; c0 < BN; c0 += 64) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_base + (uint32_t)c0, r);
+            if (sub >= nck) release(&tmem_empty_bar[acc]);            // a narrow tile leaves this warp without a chunk
+            for (int c = sub; c < nck; c += EPI_SUBS) {
+                const int c0 = c * CW;
+                uint32_t r[16];
+                tmem_ld_32x16(t_base + (uint32_t)c0, r);
+                const int col = n_tile * BN + c0;
+                float4 bv[4];
+                load_vec16(bv, p.bias + col);
                 if (lane == 0) bulk_wait_group_read<0>();             // the store that last used the box has read it
                 tmem_ld_wait();
-                if (c0 + 64 >= BN) {                                  // this warp's share of the accumulator is read
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {                                  // 8*CG arrivals release the buffer to the issuer
-                        if (CG == 1) mbar_arrive(&tmem_empty_bar[acc]);
-                        else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-                    }
-                }
-                const int col = n_tile * BN + c0;
+                if (c + EPI_SUBS >= nck) release(&tmem_empty_bar[acc]);
                 __syncwarp();
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-                if (EPI == EPI_F32 || EPI == EPI_RESID) {
-                    // 32 rows x 128 B, 128-byte swizzle: 16-byte chunk i of row r sits at chunk i ^ (r & 7)
-                    uint8_t* rowp = box + lane * 128;
+                float v[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float4 bb = __ldg(b4 + i);
-                        float4 v;
-                        v.x = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bb.x);
-                        v.y = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bb.y);
-                        v.z = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bb.z);
-                        v.w = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bb.w);
-                        *reinterpret_cast<float4*>(rowp + ((i ^ (lane & 7)) << 4)) = v;
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    v[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bv[i].x);
+                    v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bv[i].y);
+                    v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bv[i].z);
+                    v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bv[i].w);
+                }
+                if (EPI == EPI_F32 || EPI == EPI_RESID) {
+                    // one box of 32 rows x 64 B
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        sts128(box_s + box_off_f32(lane, i), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -610,53 +654,21 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                         bulk_commit_group();
                     }
                 } else {
-                    // fp16 hi/lo outputs.  Wide boxes (GELU_SPLIT, PLANES with 32-column heads): two boxes of
-                    // 32 rows x 64 B (hi, lo), 64-byte swizzle: chunk i of row r at i ^ ((r >> 1) & 3).
-                    // Narrow boxes (PLANES with 48-column heads): per 16-column piece p one box of 32 rows x 32 B,
-                    // 32-byte swizzle (chunk i of row r at i ^ ((r >> 2) & 1)), hi at p * 1024 and lo at 2048 + p * 1024.
-                    const bool narrow = EPI == EPI_PLANES && p.plane_pw == 16;
+                    // fp16 hi / lo outputs: two boxes of 32 rows x 32 B
+                    if (EPI == EPI_GELU_SPLIT) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float4 b0 = __ldg(b4 + 2 * i), b1 = __ldg(b4 + 2 * i + 1);
-                        float v[8];
-                        v[0] = fmaf(__uint_as_float(r[8 * i + 0]), oscale, b0.x);
-                        v[1] = fmaf(__uint_as_float(r[8 * i + 1]), oscale, b0.y);
-                        v[2] = fmaf(__uint_as_float(r[8 * i + 2]), oscale, b0.z);
-                        v[3] = fmaf(__uint_as_float(r[8 * i + 3]), oscale, b0.w);
-                        v[4] = fmaf(__uint_as_float(r[8 * i + 4]), oscale, b1.x);
-                        v[5] = fmaf(__uint_as_float(r[8 * i + 5]), oscale, b1.y);
-                        v[6] = fmaf(__uint_as_float(r[8 * i + 6]), oscale, b1.z);
-                        v[7] = fmaf(__uint_as_float(r[8 * i + 7]), oscale, b1.w);
-                        if (EPI == EPI_GELU_SPLIT) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
-                        }
-                        uint2 h0, l0, h1, l1;
-                        split_pair_sat(v[0], v[1], h0.x, l0.x);
-                        split_pair_sat(v[2], v[3], h0.y, l0.y);
-                        split_pair_sat(v[4], v[5], h1.x, l1.x);
-                        split_pair_sat(v[6], v[7], h1.y, l1.y);
-                        const int off = narrow ? (i >> 1) * 1024 + lane * 32 + (((i & 1) ^ ((lane >> 2) & 1)) << 4)
-                                               : lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4);
-                        *reinterpret_cast<uint4*>(box + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                        *reinterpret_cast<uint4*>(box + 2048 + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                        for (int e = 0; e < 16; ++e) v[e] = gelu_erf_fast(v[e]);
                     }
+                    stage_split16(box_s, lane, v);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
                         if (EPI == EPI_GELU_SPLIT) {
                             tma_store_2d(&tm_out0, box, col, row0);
-                            tma_store_2d(&tm_out1, box + 2048, col, row0);
-                        } else if (!narrow) {
-                            tma_store_3d(&tm_out0, box, 0, row0, col / 32);
-                            tma_store_3d(&tm_out1, box + 2048, 0, row0, col / 32);
-                        } else {
-#pragma unroll
-                            for (int pc = 0; pc < 2; ++pc) {
-                                const int cp = col + 16 * pc;
-                                tma_store_3d(&tm_out0, box + pc * 1024, cp % p.hds, row0, cp / p.hds);
-                                tma_store_3d(&tm_out1, box + 2048 + pc * 1024, cp % p.hds, row0, cp / p.hds);
-                            }
+                            tma_store_2d(&tm_out1, box + 1024, col, row0);
+                        } else {                                      // head planes: 16 columns never straddle a plane (hds % 16 == 0)
+                            tma_store_3d(&tm_out0, box, col % p.hds, row0, col / p.hds);
+                            tma_store_3d(&tm_out1, box + 1024, col % p.hds, row0, col / p.hds);
                         }
                         bulk_commit_group();
                     }
@@ -722,22 +734,13 @@ __device__ __forceinline__ void umma_f16_ts2(uint32_t tmem_d, uint32_t tmem_a, u
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t r[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-
-// 32 accumulator columns -> bias + GELU -> 16 packed fp16 hi pairs and 16 lo pairs
-__device__ __forceinline__ void mlp_gelu_split32(const uint32_t (&r)[32], const float* bias, float oscale, uint32_t (&hi)[16],
-                                                 uint32_t (&lo)[16]) {
-    float4 bv[8];
-    load_vec32(bv, bias);
+// 16 accumulator columns -> bias + GELU -> 8 packed fp16 hi pairs and 8 lo pairs
+__device__ __forceinline__ void mlp_gelu_split16(const uint32_t (&r)[16], const float* bias, float oscale, uint32_t (&hi)[8],
+                                                 uint32_t (&lo)[8]) {
+    float4 bv[4];
+    load_vec16(bv, bias);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 4; ++e) {
         const float v0 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 0]), oscale, bv[e].x));
         const float v1 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 1]), oscale, bv[e].y));
         const float v2 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 2]), oscale, bv[e].z));
@@ -754,14 +757,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                  const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_o_hi,
                  const __grid_constant__ CUtensorMap tm_o_lo, const MlpParams p) {
     constexpr int CG = 2;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ float ln_xch[128 * 2];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ float ln_xch[128 * EPI_SUBS];
     __shared__ __align__(8) uint64_t w_full[MAX_STAGES], w_empty[MAX_STAGES];
     __shared__ __align__(8) uint64_t a_full, a_empty, acc2_full, acc2_empty;
     __shared__ __align__(8) uint64_t acc1_full[2], h_full[2];
     __shared__ uint32_t tmem_base_slot;
 
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw;
     uint8_t* smem_a = smem;                                           // [kb][hi, lo][128 rows x 128 B]
     uint8_t* smem_w = smem_a + (size_t)p.kb * 2 * MLP_A_BOX_BYTES;    // weight stage ring
     uint8_t* smem_box = smem_w + (size_t)p.stages * MLP_STAGE_BYTES;  // epilogue staging, 4 KB per warp
@@ -778,6 +781,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
+        if (smem_u32(smem_raw) & 1023u) {
+            printf("pafuse: dynamic shared memory is not 1024-byte aligned\n");
+            asm volatile("trap;");
+        }
         prefetch_tensormap(&tm_a_hi); prefetch_tensormap(&tm_a_lo);
         prefetch_tensormap(&tm_w1_hi); prefetch_tensormap(&tm_w1_lo);
         prefetch_tensormap(&tm_w2_hi); prefetch_tensormap(&tm_w2_lo);
@@ -808,6 +815,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const uint32_t tmem_base = tmem_base_slot;
     pdl_wait();
 
+    if (warp < EPI_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 " PAFUSE_REGS_CTRL ";");
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0 && n_local > 0) {
@@ -944,10 +953,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 }
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " PAFUSE_REGS_EPI ";");
         // ===================== epilogue warps: GELU per chunk, then residual + LayerNorms per tile =====================
         const int q = warp & 3;                                       // TMEM lane quarter == warp % 4
-        const int half = (warp - EPI_WARP0) >> 2;                     // which half of the chunk's columns
+        const int sub = (warp - EPI_WARP0) >> 2;                      // which quarter of the chunk's columns
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const float oscale = p.out_scale;
         uint8_t* box = smem_box + (warp - EPI_WARP0) * STG_WARP_BYTES;
@@ -959,37 +970,38 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 const int hc = chunk_width(j);
                 const uint32_t b = g & 1u, use = g >> 1;
                 const uint32_t buf = tmem_base + lane_sel + (uint32_t)MLP_TM_BUF + b * 128u;
-                const int c_first = half * (hc / 2);                  // this warp's columns of the chunk: hc / 2 of them
+                const int wcols = hc / EPI_SUBS;                      // this warp's columns of the chunk: 32, or 16 for a 64-wide chunk
+                const int c_first = sub * wcols;
                 const float* bias = p.bias1 + j * MLP_HC + c_first;
                 mbar_wait(&acc1_full[b], use & 1u);
                 tcgen05_fence_after();
-                uint32_t r0[32], r1[32];
-                tmem_ld_32x32(buf + (uint32_t)c_first, r0);
-                if (hc == MLP_HC) tmem_ld_32x32(buf + (uint32_t)c_first + 32u, r1);
+                uint32_t r0[16], r1[16];
+                tmem_ld_32x16(buf + (uint32_t)c_first, r0);
+                if (hc == MLP_HC) tmem_ld_32x16(buf + (uint32_t)c_first + 16u, r1);
                 tmem_ld_wait();
-                // h goes over acc1 in place, and this warp's lo columns are the other warp's accumulator columns
-                // (and its hi columns ours): both warps of the lane quarter must have read before either writes
-                pair_bar_sync(1 + q);
-                uint32_t hi[16], lo[16];
+                // h goes over acc1 in place, and this warp's hi / lo columns are other warps' accumulator columns:
+                // all warps of the lane quarter must have read before any of them writes
+                quarter_bar_sync(1 + q);
+                uint32_t hi[8], lo[8];
                 const uint32_t hi_addr = buf + (uint32_t)(c_first / 2), lo_addr = hi_addr + (uint32_t)(hc / 2);
-                mlp_gelu_split32(r0, bias, oscale, hi, lo);
-                tmem_st_32x16(hi_addr, hi);
-                tmem_st_32x16(lo_addr, lo);
+                mlp_gelu_split16(r0, bias, oscale, hi, lo);
+                tmem_st_32x8(hi_addr, hi);
+                tmem_st_32x8(lo_addr, lo);
                 if (hc == MLP_HC) {
-                    mlp_gelu_split32(r1, bias + 32, oscale, hi, lo);
-                    tmem_st_32x16(hi_addr + 16u, hi);
-                    tmem_st_32x16(lo_addr + 16u, lo);
+                    mlp_gelu_split16(r1, bias + 16, oscale, hi, lo);
+                    tmem_st_32x8(hi_addr + 8u, hi);
+                    tmem_st_32x8(lo_addr + 8u, lo);
                 }
                 tmem_st_wait_all();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&h_full[b], 0);
             }
-            float4 xr[8];
-            ln_fetch_x(p.ep, xr, row0, half * 32, lane);              // in flight while the last G2 finishes
+            float4 xr[4];
+            if (sub * CW < C) ln_fetch_x(p.ep, xr, row0, sub * CW, lane);   // in flight while the last G2 finishes
             mbar_wait(&acc2_full, (uint32_t)(i & 1));
             tcgen05_fence_after();
-            epilogue_resid_ln<CG>(p.ep, tm_x, tm_o_hi, tm_o_lo, box, ln_xch, tmem_base + lane_sel, row0, q, half, lane, C,
+            epilogue_resid_ln<CG>(p.ep, tm_x, tm_o_hi, tm_o_lo, box, ln_xch, tmem_base + lane_sel, row0, q, sub, lane, C,
                                   oscale, &acc2_empty, xr);
         }
         if (lane == 0) bulk_wait_group<0>();
@@ -1023,15 +1035,15 @@ int make_map_f16(CUtensorMap* map, const void* ptr, long long rows, int K, int b
     return 0;
 }
 
-// output boxes of the epilogue: 32 columns x 32 rows, swizzle = the 128 (fp32) / 64 (fp16) bytes of one box row
+// output boxes of the epilogue: CW = 16 columns x 32 rows, swizzle = the 64 (fp32) / 32 (fp16) bytes of one box row
 int make_map_out(CUtensorMap* map, const void* ptr, long long rows, int N, bool f32) {
     cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)N * (f32 ? 4 : 2)};
-    cuuint32_t box[2] = {32, 32};
+    cuuint32_t box[2] = {(cuuint32_t)CW, 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                           const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled(out) failed (%d) rows=%lld N=%d ptr=%p", (int)r, rows, N, ptr);
@@ -1040,14 +1052,14 @@ int make_map_out(CUtensorMap* map, const void* ptr, long long rows, int N, bool 
     return 0;
 }
 
-// head planes [24][rows_cap][hds] fp16: box = pw columns x 32 rows of one plane
-int make_map_planes(CUtensorMap* map, const void* ptr, long long rows_cap, int hds, int pw) {
+// head planes [24][rows_cap][hds] fp16: box = CW columns x 32 rows of one plane
+int make_map_planes(CUtensorMap* map, const void* ptr, long long rows_cap, int hds) {
     cuuint64_t dims[3] = {(cuuint64_t)hds, (cuuint64_t)rows_cap, 24};
     cuuint64_t strides[2] = {(cuuint64_t)hds * 2, (cuuint64_t)rows_cap * hds * 2};
-    cuuint32_t box[3] = {(cuuint32_t)pw, 32, 1};
+    cuuint32_t box[3] = {(cuuint32_t)CW, 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, pw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled(planes) failed (%d) rows_cap=%lld hds=%d ptr=%p", (int)r, rows_cap, hds, ptr);
@@ -1070,8 +1082,12 @@ int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& 
     if (!configured[dev]) {
         cudaFuncAttributes fa;
         PAFUSE_CUDA_OK(cudaFuncGetAttributes(&fa, kern));              // static shared memory counts against the 227 KiB
-        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            SMEM_LIMIT - (int)fa.sharedSizeBytes));
+        const int static_window = ((int)fa.sharedSizeBytes + 1023) / 1024 * 1024;
+        if (static_window > (EPI == EPI_RESID_LN ? SMEM_SLACK_LN : SMEM_SLACK)) {
+            set_last_error("gemm: kernel has %d bytes of static shared memory, the ring was sized for less", (int)fa.sharedSizeBytes);
+            return -1;
+        }
+        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - static_window));
         configured[dev] = true;
     }
     PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(NUM_THREADS), (size_t)smem, st, CG, ah, al, wh, wl, o0, o1,
@@ -1091,7 +1107,7 @@ int launch_mode(bool wres, const CUtensorMap& ah, const CUtensorMap& al, const C
 template <int CG>
 int launch_cg(const GemmArgs& g, cudaStream_t st) {
     const int BN = gemm_pick_block_n(g.N);
-    if (BN < 32 || BN % 32 != 0 || g.K % 8 != 0 || g.N % 8 != 0) {
+    if (BN < 32 || BN % 32 != 0 || g.K % 8 != 0 || g.N % CW != 0) {
         set_last_error("gemm: unsupported shape N=%d K=%d (block_n=%d)", g.N, g.K, BN);
         return -1;
     }
@@ -1105,7 +1121,6 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     kp.out_scale = g.out_scale;
     kp.bias = g.bias;
     kp.hds = g.planes.hds;
-    kp.plane_pw = g.planes.hds % 32 == 0 ? 32 : 16;
     kp.ln = g.ln;
     if (g.epilogue == EPI_RESID_LN) {
         if (!gemm_can_fuse_ln(g.N) || kp.n_tiles != 1 || !g.ln.x || g.ln.x != g.out_f32 || !g.ln.g1 || !g.ln.b1 ||
@@ -1162,8 +1177,8 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
             set_last_error("gemm: bad head planes (hds=%d N=%d rows_cap=%lld M=%lld)", g.planes.hds, g.N, g.planes.rows_cap, g.M);
             return -1;
         }
-        if (int rc = make_map_planes(&o0, g.planes.hi, g.planes.rows_cap, g.planes.hds, kp.plane_pw)) return rc;
-        if (int rc = make_map_planes(&o1, g.planes.lo, g.planes.rows_cap, g.planes.hds, kp.plane_pw)) return rc;
+        if (int rc = make_map_planes(&o0, g.planes.hi, g.planes.rows_cap, g.planes.hds)) return rc;
+        if (int rc = make_map_planes(&o1, g.planes.lo, g.planes.rows_cap, g.planes.hds)) return rc;
     } else if (g.epilogue == EPI_GELU_SPLIT) {
         if (int rc = make_map_out(&o0, g.out_hi, g.M, g.N, false)) return rc;
         if (int rc = make_map_out(&o1, g.out_lo, g.M, g.N, false)) return rc;
@@ -1172,7 +1187,7 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
         o1 = o0;
     }
     if (g.epilogue != EPI_RESID_LN) o2 = o0;
-    const int smem = kp.w_res_bytes + kp.stages * kp.stage_bytes + STG_BYTES + 1024;
+    const int smem = kp.w_res_bytes + kp.stages * kp.stage_bytes + STG_BYTES;
     int grid;
     if (wres) {
         grid = kp.slots * kp.n_tiles * CG;
@@ -1222,12 +1237,12 @@ int launch_mlp(const MlpArgs& g, cudaStream_t st) {
     if (!max_dyn_dev[dev]) {
         cudaFuncAttributes fa;
         PAFUSE_CUDA_OK(cudaFuncGetAttributes(&fa, kern));
-        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            SMEM_LIMIT - (int)fa.sharedSizeBytes));
-        max_dyn_dev[dev] = SMEM_LIMIT - (int)fa.sharedSizeBytes;
+        const int static_window = ((int)fa.sharedSizeBytes + 1023) / 1024 * 1024;
+        PAFUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - static_window));
+        max_dyn_dev[dev] = SMEM_LIMIT - static_window;
     }
     const int max_dyn = max_dyn_dev[dev];
-    const int fixed = 1024 + mp.kb * 2 * MLP_A_BOX_BYTES + STG_BYTES;
+    const int fixed = mp.kb * 2 * MLP_A_BOX_BYTES + STG_BYTES;
     int stages = (max_dyn - fixed) / MLP_STAGE_BYTES;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) {
