@@ -124,10 +124,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // two values -> packed fp16 hi pair and lo pair.  No range clamp: probabilities are in [0,1], and the
 // attention output is a convex combination of V rows the GEMM epilogue already saturated to fp16 range.
-__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+__device__ __forceinline__ void split_pair2(float2 v, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(v.x, v.y);
+    const float2 d = ffma2(__half22float2(h), splat2(-1.0f), v);       // v - hi, exact
+    const __half2 l = __floats2half2_rn(d.x, d.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -387,19 +387,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                             if (k * 32 + i < L) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[k * 32 + i]));
                     }
                 const float moff = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
-                // p = exp2(s*c - m*c), row sum, fp16 hi/lo
-                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                // p = exp2(s*c - m*c), row sum, fp16 hi/lo -- on packed pairs (FFMA2 / FADD2, common.cuh): the softmax
+                // groups are bound by instruction issue and latency, not by the FMA pipe
+                float2 s2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+                const float2 sc2 = splat2(sc), nm2 = splat2(-moff);
 #pragma unroll
                 for (int k = 0; k < NCH_MAX; ++k)
                     if (k < nch) {
                         uint32_t hi16[16], lo16[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            float p0 = 0.f, p1 = 0.f;
-                            if (k * 32 + 2 * i < L) p0 = fast_exp2(fmaf(__uint_as_float(sv[k * 32 + 2 * i]), sc, -moff));
-                            if (k * 32 + 2 * i + 1 < L) p1 = fast_exp2(fmaf(__uint_as_float(sv[k * 32 + 2 * i + 1]), sc, -moff));
-                            s4[i & 3] += p0 + p1;
-                            split_pair(p0, p1, hi16[i], lo16[i]);
+                            float2 pr = ffma2(make_float2(__uint_as_float(sv[k * 32 + 2 * i]), __uint_as_float(sv[k * 32 + 2 * i + 1])),
+                                              sc2, nm2);
+                            pr.x = k * 32 + 2 * i < L ? fast_exp2(pr.x) : 0.f;          // compile-time masks for LT != 0
+                            pr.y = k * 32 + 2 * i + 1 < L ? fast_exp2(pr.y) : 0.f;
+                            s2[i & 1] = fadd2(s2[i & 1], pr);
+                            split_pair2(pr, hi16[i], lo16[i]);
                         }
                         if (SEP && k == 0 && it >= 2) {
                             // P of this unit overwrites P of unit it-2: its PV must have retired (it ran during the
@@ -411,7 +414,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                         tmem_st_32x16(phi_addr + (uint32_t)((c0 + k) * 16), hi16);
                         tmem_st_32x16(plo_addr + (uint32_t)((c0 + k) * 16), lo16);
                     }
-                sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                sum = (s2[0].x + s2[0].y) + (s2[1].x + s2[1].y);
                 if (!SEP) zero_other_groups();
                 tmem_st_wait();
             }
@@ -439,7 +442,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     if (HDP == 64) tmem_ld_32x32(o_addr + (uint32_t)(a * HDP) + 32u, oa + 32);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < HDP; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) + __uint_as_float(oa[i]));
+                    for (int i = 0; i < HDP / 2; ++i) {
+                        const float2 t = fadd2(make_float2(__uint_as_float(ov[2 * i]), __uint_as_float(ov[2 * i + 1])),
+                                               make_float2(__uint_as_float(oa[2 * i]), __uint_as_float(oa[2 * i + 1])));
+                        ov[2 * i] = __float_as_uint(t.x);
+                        ov[2 * i + 1] = __float_as_uint(t.y);
+                    }
                 }
                 tmem_ld_wait();
             }
@@ -465,11 +473,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             // O / sum -> fp16 hi/lo, once; each half goes through this warp's staging rows (pitch = row bytes + 16,
             // bank-conflict free) so that the global stores are runs of whole head slices (a lane-per-row store
             // touched 32 different sectors per instruction and cost 25 % of the kernel)
-            const float inv = 1.0f / sum;
+            const float2 inv2 = splat2(1.0f / sum);
             uint32_t oh[HDP / 2], ol[HDP / 2];
 #pragma unroll
             for (int i = 0; i < HDP / 2; ++i)
-                split_pair(__uint_as_float(ov[2 * i]) * inv, __uint_as_float(ov[2 * i + 1]) * inv, oh[i], ol[i]);
+                split_pair2(fmul2(make_float2(__uint_as_float(ov[2 * i]), __uint_as_float(ov[2 * i + 1])), inv2), oh[i], ol[i]);
             // copy-out: lane -> (row lane / cpr of the current group of rows_per_iter rows, chunk lane % cpr); the
             // per-chunk index arithmetic of the first version (64-bit multiplies per 8 bytes) cost as many
             // instructions as the softmax itself (profiles/r1h_*)

@@ -146,11 +146,15 @@ __device__ __forceinline__ void quarter_bar_sync(int id) { asm volatile("bar.syn
 // both patterns are bank-conflict free for a quarter-warp of consecutive rows
 __device__ __forceinline__ uint32_t box_off_f32(int row, int i) { return (uint32_t)(row * 64 + ((i ^ ((row >> 1) & 3)) << 4)); }
 __device__ __forceinline__ uint32_t box_off_f16(int row, int i) { return (uint32_t)(row * 32 + ((i ^ ((row >> 2) & 1)) << 4)); }
-// 16 values -> fp16 hi / lo boxes (hi at +0, lo at +1024) of this warp's staging area
-__device__ __forceinline__ void stage_split16(uint32_t box_s, int lane, const float (&v)[16]) {
+// accumulator registers 2j, 2j+1 as a packed pair
+__device__ __forceinline__ float2 pair_of(const uint32_t (&r)[16], int j) {
+    return make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+}
+// 16 values (8 pairs) -> fp16 hi / lo boxes (hi at +0, lo at +1024) of this warp's staging area
+__device__ __forceinline__ void stage_split16(uint32_t box_s, int lane, const float2 (&v)[8]) {
     uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split_pair_sat(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+    for (int i = 0; i < 8; ++i) split_pair_sat2(v[i], hi[i], lo[i]);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const uint32_t off = box_off_f16(lane, i);
@@ -252,7 +256,10 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
     };
 
     // ---- pass 1: v = x + acc * scale + bias -> tensor memory (and, when not chained, -> x)
-    float K = 0.f, S = 0.f, Q = 0.f;
+    // (all row arithmetic on packed pairs: FFMA2 / FADD2, see common.cuh)
+    const float2 osc2 = splat2(oscale);
+    float K = 0.f;
+    float2 S2 = splat2(0.f), Q2 = splat2(0.f);
     for (int ci = 0; ci < mine; ++ci) {
         const int c0 = (sub + EPI_SUBS * ci) * CW;
         uint32_t r[16];
@@ -271,22 +278,18 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         for (int i = 0; i < 4; ++i) {
             const uint32_t slot = box_s + box_off_f32(lane, i);
             const float4 xv = lds128(slot);
-            float4 v;
-            v.x = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bv[i].x) + xv.x;
-            v.y = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bv[i].y) + xv.y;
-            v.z = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bv[i].z) + xv.z;
-            v.w = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bv[i].w) + xv.w;
-            if (ci == 0 && i == 0) K = v.x;
-            {
-                const float d0 = v.x - K, d1 = v.y - K, d2 = v.z - K, d3 = v.w - K;
-                S += (d0 + d1) + (d2 + d3);
-                Q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, Q))));
-            }
-            r[4 * i + 0] = __float_as_uint(v.x);
-            r[4 * i + 1] = __float_as_uint(v.y);
-            r[4 * i + 2] = __float_as_uint(v.z);
-            r[4 * i + 3] = __float_as_uint(v.w);
-            if (!chained) sts128(slot, v);
+            const float2 va = fadd2(ffma2(pair_of(r, 2 * i), osc2, make_float2(bv[i].x, bv[i].y)), make_float2(xv.x, xv.y));
+            const float2 vb = fadd2(ffma2(pair_of(r, 2 * i + 1), osc2, make_float2(bv[i].z, bv[i].w)), make_float2(xv.z, xv.w));
+            if (ci == 0 && i == 0) K = va.x;
+            const float2 nK = splat2(-K);
+            const float2 da = fadd2(va, nK), db = fadd2(vb, nK);
+            S2 = fadd2(S2, fadd2(da, db));
+            Q2 = ffma2(da, da, ffma2(db, db, Q2));
+            r[4 * i + 0] = __float_as_uint(va.x);
+            r[4 * i + 1] = __float_as_uint(va.y);
+            r[4 * i + 2] = __float_as_uint(vb.x);
+            r[4 * i + 3] = __float_as_uint(vb.y);
+            if (!chained) sts128(slot, make_float4(va.x, va.y, vb.x, vb.y));
         }
         tmem_st_32x16(t_base + (uint32_t)c0, r);
         if (!chained) {
@@ -300,14 +303,14 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
     }
     tmem_st_wait_all();
     float mean, rstd;
-    merge_stats(K, S, Q, chained ? f.eps0 : f.eps1, mean, rstd);
+    merge_stats(K, S2.x + S2.y, Q2.x + Q2.y, chained ? f.eps0 : f.eps1, mean, rstd);
 
     if (chained) {
         // ---- y = LN(v; g0, b0) [+ add_f[f]] -> x and tensor memory
-        const float mr = -mean * rstd;
+        const float2 rstd2 = splat2(rstd), mr2 = splat2(-mean * rstd);
         const long long row = (long long)row0 + lane;
         const float* addr = f.add_f ? f.add_f + (size_t)((row / f.J) % f.F) * N : nullptr;
-        K = 0.f; S = 0.f; Q = 0.f;
+        K = 0.f; S2 = splat2(0.f); Q2 = splat2(0.f);
         for (int ci = 0; ci < mine; ++ci) {
             const int c0 = (sub + EPI_SUBS * ci) * CW;
             uint32_t r[16];
@@ -316,34 +319,34 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
             load_vec16(gv, f.g0 + c0);
             load_vec16(bv, f.b0 + c0);
             tmem_ld_wait();
-            float4 y[4];
+            float2 y[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                y[i].x = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), rstd, mr), gv[i].x, bv[i].x);
-                y[i].y = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), rstd, mr), gv[i].y, bv[i].y);
-                y[i].z = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), rstd, mr), gv[i].z, bv[i].z);
-                y[i].w = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), rstd, mr), gv[i].w, bv[i].w);
+                y[2 * i] = ffma2(ffma2(pair_of(r, 2 * i), rstd2, mr2), make_float2(gv[i].x, gv[i].y), make_float2(bv[i].x, bv[i].y));
+                y[2 * i + 1] = ffma2(ffma2(pair_of(r, 2 * i + 1), rstd2, mr2), make_float2(gv[i].z, gv[i].w), make_float2(bv[i].z, bv[i].w));
             }
             if (addr) {                                               // Temporal_pos_embed (after STE block 0 only)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 a = __ldg(reinterpret_cast<const float4*>(addr + c0) + i);
-                    y[i].x += a.x; y[i].y += a.y; y[i].z += a.z; y[i].w += a.w;
+                    y[2 * i] = fadd2(y[2 * i], make_float2(a.x, a.y));
+                    y[2 * i + 1] = fadd2(y[2 * i + 1], make_float2(a.z, a.w));
                 }
             }
             if (lane == 0) bulk_wait_group_read<0>();
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (ci == 0 && i == 0) K = y[i].x;
-                const float d0 = y[i].x - K, d1 = y[i].y - K, d2 = y[i].z - K, d3 = y[i].w - K;
-                S += (d0 + d1) + (d2 + d3);
-                Q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, Q))));
-                sts128(box_s + box_off_f32(lane, i), y[i]);
-                r[4 * i + 0] = __float_as_uint(y[i].x);
-                r[4 * i + 1] = __float_as_uint(y[i].y);
-                r[4 * i + 2] = __float_as_uint(y[i].z);
-                r[4 * i + 3] = __float_as_uint(y[i].w);
+                if (ci == 0 && i == 0) K = y[0].x;
+                const float2 nK = splat2(-K);
+                const float2 da = fadd2(y[2 * i], nK), db = fadd2(y[2 * i + 1], nK);
+                S2 = fadd2(S2, fadd2(da, db));
+                Q2 = ffma2(da, da, ffma2(db, db, Q2));
+                sts128(box_s + box_off_f32(lane, i), make_float4(y[2 * i].x, y[2 * i].y, y[2 * i + 1].x, y[2 * i + 1].y));
+                r[4 * i + 0] = __float_as_uint(y[2 * i].x);
+                r[4 * i + 1] = __float_as_uint(y[2 * i].y);
+                r[4 * i + 2] = __float_as_uint(y[2 * i + 1].x);
+                r[4 * i + 3] = __float_as_uint(y[2 * i + 1].y);
             }
             tmem_st_32x16(t_base + (uint32_t)c0, r);
             fence_proxy_async_smem();
@@ -354,12 +357,12 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
             }
         }
         tmem_st_wait_all();
-        merge_stats(K, S, Q, f.eps1, mean, rstd);
+        merge_stats(K, S2.x + S2.y, Q2.x + Q2.y, f.eps1, mean, rstd);
     }
 
     // ---- a = LN(row values in tensor memory; g1, b1) -> fp16 hi/lo boxes -> TMA stores
     {
-        const float mr = -mean * rstd;
+        const float2 rstd2 = splat2(rstd), mr2 = splat2(-mean * rstd);
         for (int ci = 0; ci < mine; ++ci) {
             const int c0 = (sub + EPI_SUBS * ci) * CW;
             uint32_t r[16];
@@ -368,13 +371,11 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
             load_vec16(gv, f.g1 + c0);
             load_vec16(bv, f.b1 + c0);
             tmem_ld_wait();
-            float v[16];
+            float2 v[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                v[4 * i + 0] = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), rstd, mr), gv[i].x, bv[i].x);
-                v[4 * i + 1] = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), rstd, mr), gv[i].y, bv[i].y);
-                v[4 * i + 2] = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), rstd, mr), gv[i].z, bv[i].z);
-                v[4 * i + 3] = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), rstd, mr), gv[i].w, bv[i].w);
+                v[2 * i] = ffma2(ffma2(pair_of(r, 2 * i), rstd2, mr2), make_float2(gv[i].x, gv[i].y), make_float2(bv[i].x, bv[i].y));
+                v[2 * i + 1] = ffma2(ffma2(pair_of(r, 2 * i + 1), rstd2, mr2), make_float2(gv[i].z, gv[i].w), make_float2(bv[i].z, bv[i].w));
             }
             if (lane == 0) bulk_wait_group_read<0>();                 // the store that last used the box has read it
             __syncwarp();
@@ -633,19 +634,18 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 tmem_ld_wait();
                 if (c + EPI_SUBS >= nck) release(&tmem_empty_bar[acc]);
                 __syncwarp();
-                float v[16];
+                float2 v[8];                                          // packed pairs: FFMA2 (common.cuh)
+                const float2 osc2 = splat2(oscale);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    v[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), oscale, bv[i].x);
-                    v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), oscale, bv[i].y);
-                    v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), oscale, bv[i].z);
-                    v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), oscale, bv[i].w);
+                    v[2 * i] = ffma2(pair_of(r, 2 * i), osc2, make_float2(bv[i].x, bv[i].y));
+                    v[2 * i + 1] = ffma2(pair_of(r, 2 * i + 1), osc2, make_float2(bv[i].z, bv[i].w));
                 }
                 if (EPI == EPI_F32 || EPI == EPI_RESID) {
                     // one box of 32 rows x 64 B
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        sts128(box_s + box_off_f32(lane, i), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                        sts128(box_s + box_off_f32(lane, i), make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y));
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -657,7 +657,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     // fp16 hi / lo outputs: two boxes of 32 rows x 32 B
                     if (EPI == EPI_GELU_SPLIT) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = gelu_erf_fast(v[e]);
+                        for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast2(v[e]);
                     }
                     stage_split16(box_s, lane, v);
                     fence_proxy_async_smem();
@@ -739,14 +739,13 @@ __device__ __forceinline__ void mlp_gelu_split16(const uint32_t (&r)[16], const 
                                                  uint32_t (&lo)[8]) {
     float4 bv[4];
     load_vec16(bv, bias);
+    const float2 osc2 = splat2(oscale);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float v0 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 0]), oscale, bv[e].x));
-        const float v1 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 1]), oscale, bv[e].y));
-        const float v2 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 2]), oscale, bv[e].z));
-        const float v3 = gelu_erf_fast(fmaf(__uint_as_float(r[4 * e + 3]), oscale, bv[e].w));
-        split_pair_sat(v0, v1, hi[2 * e], lo[2 * e]);
-        split_pair_sat(v2, v3, hi[2 * e + 1], lo[2 * e + 1]);
+        const float2 va = gelu_erf_fast2(ffma2(pair_of(r, 2 * e), osc2, make_float2(bv[e].x, bv[e].y)));
+        const float2 vb = gelu_erf_fast2(ffma2(pair_of(r, 2 * e + 1), osc2, make_float2(bv[e].z, bv[e].w)));
+        split_pair_sat2(va, hi[2 * e], lo[2 * e]);
+        split_pair_sat2(vb, hi[2 * e + 1], lo[2 * e + 1]);
     }
 }
 
