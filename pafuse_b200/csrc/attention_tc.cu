@@ -20,12 +20,19 @@
 // [which(q,k,v) * 8 + head][token][hds], hds = head_dim rounded up to 16; the TMA box is HDP = 64 / 32
 // columns wide (one 128- / 64-byte swizzle span per tile row), columns past hds are zero-filled too.
 //
-//   warps 0,3  TMA producers, one per ring stage (warp 0 also allocates the tensor memory): a Q/K ring and a V
-//              ring, two stages each, so the next unit's Q,K are in flight while this unit's softmax and PV run
-//   warps 1,2  MMA issuers, one per stage:   S = QK^T, O = PV, two units in flight (one per softmax group)
+// NSTG = 2 or 3 units in flight per SM ("stages": each has its tensor-memory region, its TMA producer warp, its MMA
+// issuer warp and its softmax warpgroup).  Two stages: 12 warps --
+//   warps 0,3  TMA producers, one per stage (warp 0 also allocates the tensor memory): a Q/K ring and a V
+//              ring, so the next unit's Q,K are in flight while this unit's softmax and PV run
+//   warps 1,2  MMA issuers, one per stage:   S = QK^T, O = PV
 //   warps 4-7  softmax group 0 (units 0, 2, 4, ... of this CTA), TMEM stage 0
 //   warps 8-11 softmax group 1 (units 1, 3, 5, ...), TMEM stage 1   (setmaxnreg: 216 registers each,
 //              taken from the control warpgroup)
+// Three stages (round 2, opt-in PAFUSE_ATT_STAGES=3; the aliased layout of the narrow heads needs 128 + 32 columns per
+// stage, so three fit): 20 warps -- producers 0-2, issuers 3-5, softmax groups at warps 8-11 / 12-15 / 16-19 (128
+// registers each).  A unit is a latency chain (TMA -> QK^T -> softmax -> 24 small PV MMAs -> output) and the softmax
+// groups spend a third of their time waiting for the tensor pipe (profiles/r2h_hotlines_face_attention.txt); the third
+// unit fills those waits but costs the operand prefetch distance (one ring slot per stage) and measured slower.
 //              thread = tile row = TMEM lane: scores of the row's group read once into registers, max,
 //              exp2, sum, fp16 hi/lo -> TMEM; then O -> registers -> 1/sum -> fp16 hi/lo -> per-warp staging
 //              rows in shared memory -> 16-byte global stores of whole head slices of [token, C]
@@ -40,7 +47,7 @@ namespace pafuse {
 namespace {
 
 constexpr int TILE_ROWS = 128;
-constexpr int ATT_THREADS = 384;
+__host__ __device__ constexpr int att_threads(int nstg) { return nstg == 2 ? 384 : 640; }
 // TMEM columns, two layouts (AttnTcParams::tm_*):
 //   aliased (SEP = false): stage s holds S (fp32, 128 columns) at s*128, overwritten in place by P_hi (64 columns
 //     of packed fp16 pairs) and P_lo (next 64); O (fp32, HDP columns) at 256 + s*64.  QK^T of unit i+2 can only
@@ -133,8 +140,8 @@ __device__ __forceinline__ void split_pair2(float2 v, uint32_t& hi, uint32_t& lo
 }
 
 // HDP: tile row width in fp16 elements (64 / 32).  LT: compile-time group length (0 = use p.L; NCH_MAX chunks)
-template <int HDP, int LT, bool SEP>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int HDP, int LT, bool SEP, int NSTG>
+__global__ void __launch_bounds__(att_threads(NSTG), 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                     const AttnTcParams p) {
     constexpr int ROWB = HDP * 2;                              // bytes per tile row = swizzle span
@@ -146,10 +153,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     // operand ring slots: unit `it` loads into slot it % NS.  Two tensor-memory stages bound the units in flight, but
     // the 48 KB stages of the narrow heads leave room for four slots, so Q, K, V are requested three units ahead
     // instead of one and their DRAM latency no longer sits inside the unit's QK -> softmax -> PV chain.
-    constexpr int NS = HDP == 32 ? 4 : 2;
+    // A ring slot must always be reused by the SAME stage (NS a multiple of NSTG): the mbarrier waits are parity waits,
+    // and a producer of another stage that is two uses behind the slot's barrier would take the completion of use k-2 for
+    // that of use k (observed with NSTG = 3 on 4 shared slots: a fast stage lapped a slow one and overwrote live tiles).
+    constexpr int NS = NSTG == 3 ? 3 : (HDP == 32 ? 4 : 2);
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t qk_full[NS], qk_empty[NS], v_full[NS], v_empty[NS];
-    __shared__ __align__(8) uint64_t s_full[2], s_empty[2], p_full[2], o_full[2], o_empty[2];
+    __shared__ __align__(8) uint64_t s_full[NSTG], s_empty[NSTG], p_full[NSTG], o_full[NSTG], o_empty[NSTG];
+    constexpr int ATT_THREADS = att_threads(NSTG);
+    constexpr int CTRL_WARPS = NSTG == 2 ? 4 : 8;              // warps before the softmax groups (whole warpgroups)
     __shared__ uint32_t tmem_base_slot;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -185,7 +197,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             mbar_init(&v_full[s], 1);
             mbar_init(&v_empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NSTG; ++s) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], n_live);
             mbar_init(&p_full[s], n_live);                     // one lane per live warp of the stage's softmax group
@@ -204,15 +216,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     const uint32_t tmem_base = tmem_base_slot;
     pdl_wait();                                                // the planes come from the preceding kernel
 
-    if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");                   // control warpgroup donates registers ...
-    if (warp == 0 || warp == 3) {
+    // stage a control warp serves: NSTG == 2: producers 0,3 / issuers 1,2; NSTG == 3: producers 0-2 / issuers 3-5
+    const bool is_producer = NSTG == 2 ? (warp == 0 || warp == 3) : warp < 3;
+    const bool is_issuer = NSTG == 2 ? (warp == 1 || warp == 2) : (warp >= 3 && warp < 6);
+    const int ctrl_stage = NSTG == 2 ? (warp == 0 ? 0 : warp == 3 ? 1 : warp - 1) : warp % 3;
+    if (warp < CTRL_WARPS) {
+    if (NSTG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");    // control warpgroup(s) donate registers ...
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (is_producer) {
         // ===================== TMA producers: warp 0 feeds ring stage 0 (units 0, 2, ...), warp 3 stage 1 ==========
         // (one thread for both stages made the Q,K loads of unit i+1 queue behind the wait for PV of unit i-2)
         if (lane == 0) {
-            const int stage = warp == 0 ? 0 : 1;
+            const int stage = ctrl_stage;
             const uint32_t tile_tx = (uint32_t)(rows_box * ROWB);          // zero-filled rows count too
-            for (int it = stage; it < n_local; it += 2) {
+            for (int it = stage; it < n_local; it += NSTG) {
                 const int u = (int)blockIdx.x + it * (int)gridDim.x;
                 const int slot = it % NS;
                 const uint32_t ph = (uint32_t)(it / NS) & 1u;
@@ -247,15 +264,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 }
             }
         }
-    } else {
-        // ===================== MMA issuers: warp 1 drives stage 0, warp 2 stage 1 =====================
+    } else if (is_issuer) {
+        // ===================== MMA issuers, one per stage =====================
         // Per stage the order QK(i), PV(i), QK(i+2), PV(i+2), ... is what lets S alias P; the two stages are
         // independent, and with one issuing thread PV(i+1) used to wait behind the operands of QK(i+2).
         if (lane == 0) {
-            const int stage = warp - 1;
+            const int stage = ctrl_stage;
             const uint32_t idesc_qk = make_idesc_f16(128, (uint32_t)(key_steps * 16));
             const uint32_t idesc_pv = make_idesc_f16(128, HDP) | (1u << 16);      // B (= V) is MN-major
-            const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);   // slot of this issuer's first unit
+            const uint32_t sa = smem_u32(smem);                // ring slot 0; slot_off() below selects the unit's slot
             const uint32_t d_s = tmem_base + (uint32_t)(p.tm_s0 + stage * p.tm_stride_s);
             const uint32_t d_o = tmem_base + (uint32_t)(p.tm_o0 + stage * p.tm_stride_o);
             // n_acc = 3: the passes go to accumulators 0, 1, 2; n_acc = 2: lo*hi and hi*hi -> 0, hi*lo -> 1; n_acc = 1: all -> 0
@@ -264,15 +281,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             const uint32_t d_phi = d_s + (uint32_t)p.tm_phi_off, d_plo = d_s + (uint32_t)p.tm_plo_off;
             // Operand descriptors of this stage are loop invariants; only their 16-byte address field moves.  Built
             // inside the loops they made the single issuing thread the bottleneck of every attention variant:
-            // ~90-110 cycles per issued MMA whatever its shape (profiles/r1m_*, r1p_*).
+            // ~90-110 cycles per issued MMA whatever its shape (profiles/r1m_bench_launches.txt, profiles/r1h_hotlines_attention_sep.txt).
             const uint64_t qh0 = make_desc(sa, SBO, LAYOUT), ql0 = make_desc(sa + TILE_BYTES, SBO, LAYOUT);
             const uint64_t kh0 = make_desc(sa + 2 * TILE_BYTES, SBO, LAYOUT), kl0 = make_desc(sa + 3 * TILE_BYTES, SBO, LAYOUT);
             const uint64_t vh0 = make_desc(sa + 4 * TILE_BYTES, SBO, LAYOUT), vl0 = make_desc(sa + 5 * TILE_BYTES, SBO, LAYOUT);
             constexpr uint64_t V_STEP = (16u * ROWB) >> 4;
-            // this issuer's units it = stage, stage + 2, ... sit in slots stage, stage + 2 (mod NS): descriptor offset of a slot
-            auto slot_off = [&](int it) { return (uint64_t)(((it % NS) - stage) * (STAGE_BYTES >> 4)); };
+            // unit `it` sits in ring slot it % NS: descriptor offset of that slot
+            auto slot_off = [&](int it) { return (uint64_t)((it % NS) * (STAGE_BYTES >> 4)); };
             auto issue_qk = [&](int it) {
-                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                const uint32_t ph = (uint32_t)(it / NSTG) & 1u;
                 const int slot = it % NS;
                 const uint64_t so = slot_off(it);
                 mbar_wait(&qk_full[slot], (uint32_t)(it / NS) & 1u);
@@ -291,9 +308,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 umma_commit<1>(&s_full[stage]);
             };
             if (stage < n_local) issue_qk(stage);
-            for (int it = stage; it < n_local; it += 2) {
-                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-                if (SEP && it + 2 < n_local) issue_qk(it + 2);
+            for (int it = stage; it < n_local; it += NSTG) {
+                const uint32_t ph = (uint32_t)(it / NSTG) & 1u;
+                if (SEP && it + NSTG < n_local) issue_qk(it + NSTG);
                 const int slot = it % NS;
                 mbar_wait(&v_full[slot], (uint32_t)(it / NS) & 1u);
                 mbar_wait(&o_empty[stage], ph ^ 1);            // the softmax group has read O of unit it-2
@@ -305,7 +322,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                     // 16 keys further down the V tile / 16 fp16 keys = 8 tensor-memory columns further in P
                     // Separate accumulators per pass: the PV MMAs are tiny (N = HDP) and a chain of 3 * key_steps
                     // dependent accumulations into ONE tile ran at the pipe's latency, ~90 cycles per MMA
-                    // (profiles/r1m_*: every attention variant cost ~90-110 cycles per issued MMA).
+                    // (profiles/r1m_bench_launches.txt: every attention variant cost ~90-110 cycles per issued MMA).
                     const uint32_t first = k != 0 ? 1u : 0u;
                     umma_f16_ts(d_o, pl_a, vh, idesc_pv, first);
                     umma_f16_ts(d_o1, ph_a, vl, idesc_pv, p.n_acc >= 2 ? first : 1u);
@@ -313,14 +330,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 }
                 umma_commit<1>(&v_empty[slot]);
                 umma_commit<1>(&o_full[stage]);
-                if (!SEP && it + 2 < n_local) issue_qk(it + 2);
+                if (!SEP && it + NSTG < n_local) issue_qk(it + NSTG);
             }
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");              // ... to the two softmax warpgroups
+        if (NSTG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");   // ... to the softmax warpgroups
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");             // 8*32*40 + 12*32*128 = 59392 <= 640*96 (the CTA's register allocation)
         // ===================== softmax + output =====================
-        const int wg = (warp - 4) >> 2;                        // softmax group = TMEM stage
+        const int wg = (warp - CTRL_WARPS) >> 2;               // softmax group = TMEM stage
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;                           // tile row == TMEM lane
         // all 32 rows of a warp belong to one group (Lp is a multiple of 32)
@@ -333,7 +351,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         const uint32_t phi_addr = s_addr + (uint32_t)p.tm_phi_off, plo_addr = s_addr + (uint32_t)p.tm_plo_off;
         const uint32_t o_addr = tmem_base + lane_sel + (uint32_t)(p.tm_o0 + wg * p.tm_stride_o);
         const float sc = p.scale_log2e;
-        uint8_t* stg = smem + NS * STAGE_BYTES + (warp - 4) * p.stg_warp_bytes;  // this warp's output staging rows
+        uint8_t* stg = smem + NS * STAGE_BYTES + (warp - CTRL_WARPS) * p.stg_warp_bytes;  // this warp's output staging rows
         uint8_t* my_row = stg + lane * p.stg_pitch;
         const int n_zero_chunks = (key_steps + 1) / 2;         // 32-key chunks the PV product reads
         const int cp_row = lane / p.chunks_per_row;            // copy-out role of this lane
@@ -359,7 +377,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
         // ---- S -> P of unit `it`; returns the row sum
         auto softmax_unit = [&](int it) -> float {
-            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            const uint32_t ph = (uint32_t)(it / NSTG) & 1u;
             mbar_wait(&s_full[wg], ph);
             tcgen05_fence_after();
             float sum = 0.f;
@@ -404,11 +422,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                             s2[i & 1] = fadd2(s2[i & 1], pr);
                             split_pair2(pr, hi16[i], lo16[i]);
                         }
-                        if (SEP && k == 0 && it >= 2) {
+                        if (SEP && k == 0 && it >= NSTG) {
                             // P of this unit overwrites P of unit it-2: its PV must have retired (it ran during the
                             // output of unit it-4 and the exponentials above).  This also keeps p_full from running
                             // two phases ahead of the issuer, which would then wait for ever on a parity.
-                            mbar_wait(&o_full[wg], (uint32_t)((it - 2) >> 1) & 1u);
+                            mbar_wait(&o_full[wg], (uint32_t)((it - NSTG) / NSTG) & 1u);
                             tcgen05_fence_after();
                         }
                         tmem_st_32x16(phi_addr + (uint32_t)((c0 + k) * 16), hi16);
@@ -427,7 +445,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
         // ---- O of unit `it` / sum -> fp16 hi/lo -> global
         auto output_unit = [&](int it, float sum) {
-            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            const uint32_t ph = (uint32_t)(it / NSTG) & 1u;
             const int u = (int)blockIdx.x + it * (int)gridDim.x;
             const int tile = u >> 3, head = u & 7;
             mbar_wait(&o_full[wg], ph);
@@ -510,7 +528,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         if (!warp_live) {
             // no rows: nothing to compute, nothing to signal
         } else if (!SEP) {
-            for (int it = wg; it < n_local; it += 2) {
+            for (int it = wg; it < n_local; it += NSTG) {
                 const float sum = softmax_unit(it);
                 output_unit(it, sum);
             }
@@ -519,7 +537,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             // softmax of unit it
             float prev_sum = 1.f;
             int prev = -1;
-            for (int it = wg; it < n_local; it += 2) {
+            for (int it = wg; it < n_local; it += NSTG) {
                 const float sum = softmax_unit(it);
                 if (prev >= 0) output_unit(prev, prev_sum);
                 prev = it;
@@ -539,6 +557,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
 PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
 int g_n_acc_cap = 1;     // PAFUSE_ATT_NACC: O accumulators per stage the PV passes are spread over (measured: 1 is fastest, the extra tensor-memory reads cost more than the shorter MMA chains save)
+int g_stages = 2;        // PAFUSE_ATT_STAGES=3: three units in flight per SM where the tensor-memory layout allows it (narrow heads, aliased
+                         // layout).  Opt-in: measured SLOWER (face temporal 1265 -> 1667 us, hands temporal 543 -> 656, hands spatial 627 -> 672,
+                         // profiles/r2j_*): with three stages every stage owns ONE ring slot (slots must not be shared between stages, see the
+                         // kernel), so Q, K, V of unit i+3 are requested only when unit i has used them -- the two-stage kernel asks three units
+                         // ahead, and that prefetch distance is worth more than the third unit in flight
 int g_sep_mode = 1;      // PAFUSE_ATT_SEP: 0 aliased layout only, 1 separate when it fits (default), 2 also with one group less per tile (slower: measured)
 
 int att_init() {
@@ -553,6 +576,7 @@ int att_init() {
     g_enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     if (const char* e = getenv("PAFUSE_ATT_SEP")) g_sep_mode = atoi(e);
     if (const char* e = getenv("PAFUSE_ATT_NACC")) g_n_acc_cap = atoi(e);
+    if (const char* e = getenv("PAFUSE_ATT_STAGES")) g_stages = atoi(e);
     return 0;
 }
 
@@ -588,15 +612,15 @@ int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int h
     return 0;
 }
 
-template <int HDP, int LT, bool SEP>
+template <int HDP, int LT, bool SEP, int NSTG>
 int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, cudaStream_t st, int sms) {
-    constexpr int NS = HDP == 32 ? 4 : 2;                              // operand ring slots (see the kernel)
-    const int SMEM = NS * 6 * TILE_ROWS * HDP * 2 + 8 * p.stg_warp_bytes + 1024;
+    constexpr int NS = NSTG == 3 ? 3 : (HDP == 32 ? 4 : 2);            // operand ring slots (see the kernel)
+    const int SMEM = NS * 6 * TILE_ROWS * HDP * 2 + 4 * NSTG * p.stg_warp_bytes + 1024;
     if (SMEM > 227 * 1024) {
         set_last_error("attention_tc: head_dim %d needs %d bytes of shared memory", p.hd, SMEM);
         return -1;
     }
-    auto kern = attention_tc_kernel<HDP, LT, SEP>;
+    auto kern = attention_tc_kernel<HDP, LT, SEP, NSTG>;
     static int configured[MAX_DEVICES] = {0};                          // per template instance and per device
     const int dev = current_device_slot();
     if (configured[dev] < SMEM) {
@@ -608,7 +632,7 @@ int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& 
     // on an SM share the CTAs are placed as pairs (no cluster feature is used), so that the share keeps whole
     // TPCs and the CTA pairs of the GEMMs running next to it on other streams still find two free SMs together
     const int cluster = sms < device_sm_count() && grid % 2 == 0 ? 2 : 1;
-    PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(ATT_THREADS), (size_t)SMEM, st, cluster, mh, ml, p));
+    PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(att_threads(NSTG)), (size_t)SMEM, st, cluster, mh, ml, p));
     PAFUSE_LAUNCH_OK();
     return 0;
 }
@@ -656,14 +680,23 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
             }
         }
     }
+    // Aliased layout with the narrow heads: a stage needs 128 (S / P) + 32 (O) columns, so THREE units fit in the 512
+    // columns and run in flight (PAFUSE_ATT_STAGES=2 keeps two).
+    const bool three = !sep && hdp == 32 && g_stages >= 3;
     if (!sep) {
         p.tm_s0 = 0;
         p.tm_stride_s = 128;
         p.tm_phi_off = 0;
         p.tm_plo_off = 64;
-        p.n_acc = hdp == 32 ? 3 : 2;                               // 256 columns are left for O: 2 stages x n_acc x hdp
-        p.tm_o0 = 256;
-        p.tm_stride_o = p.n_acc * hdp;
+        if (three) {
+            p.n_acc = 1;
+            p.tm_o0 = 384;
+            p.tm_stride_o = hdp;
+        } else {
+            p.n_acc = hdp == 32 ? 3 : 2;                           // 256 columns are left for O: 2 stages x n_acc x hdp
+            p.tm_o0 = 256;
+            p.tm_stride_o = p.n_acc * hdp;
+        }
     }
     if (p.n_acc > g_n_acc_cap) p.n_acc = g_n_acc_cap < 1 ? 1 : g_n_acc_cap;
     p.hd = hd;
@@ -693,7 +726,9 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
     // the group lengths of the H3WB parts get compile-time masks; anything else runs the generic instance
 #define PAFUSE_ATT_CASE(HDPV, LV)                                                             \
     if (hdp == HDPV && (LV == 0 || L == LV))                                                  \
-        return sep ? launch_tc<HDPV, LV, true>(mh, ml, p, st, sms) : launch_tc<HDPV, LV, false>(mh, ml, p, st, sms);
+        return sep ? launch_tc<HDPV, LV, true, 2>(mh, ml, p, st, sms)                          \
+                   : (three ? launch_tc<HDPV, LV, false, (HDPV == 32 ? 3 : 2)>(mh, ml, p, st, sms) \
+                            : launch_tc<HDPV, LV, false, 2>(mh, ml, p, st, sms));
     PAFUSE_ATT_CASE(64, 24)
     PAFUSE_ATT_CASE(64, 27)
     PAFUSE_ATT_CASE(64, 0)

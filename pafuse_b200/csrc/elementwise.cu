@@ -93,13 +93,40 @@ int launch_time_mlp(const float* sinus, const float* w1, const float* b1, const 
 // apply_clamp, diffusionpose.py:193-194) and, for flip sequences (s >= R_flip_start),
 // x is negated and left/right joints are swapped on the fly (:195-198).
 // One warp per token row; lanes stride over channels.
-__global__ void embed_kernel(EmbedParams p) {
+template <int NV>
+__device__ __forceinline__ void ln_row_stats(const float4 (&v)[NV], int lane, int C, float& mean, float& rstd, float eps) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);   // lanes past C hold zeros
+    const float invC = 1.0f / (float)C;
+    mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if (4 * lane + 128 * i < C) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    rstd = 1.0f / sqrtf(warp_sum(q) * invC + eps);
+}
+
+// One warp per token row; the row lives in registers as NV float4 per lane (channels 4*lane + 128*i, the layout of
+// ln_chain_kernel): 16-byte loads of the 20 weights of four channels and of the bias / positional / time vectors (the
+// round-1 kernel did eight scalar loads per element and wrote x at 2 TB/s), one 16-byte store per four channels.  When
+// g1 is given, norm1 of STE block 0 (mixste.py:114) is applied to the row while it is in registers and its fp16 hi/lo
+// pair is written as well: the separate ln_chain launch of block 0 (a read of x and a launch per part) is gone.  The
+// arithmetic per element and the statistics are those of the two separate kernels, bit for bit.
+template <int NV>
+__global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
     pdl_launch_dependents();
     pdl_wait();
-    int warps_per_block = blockDim.x >> 5;
-    long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    if (m >= p.M) return;
-    int lane = threadIdx.x & 31;
+    // persistent warps: with one row per warp and 8 rows per block the launch was bound by block scheduling
+    // (147 K blocks of ~2 us on the face part), not by memory
+    const int warps_per_block = blockDim.x >> 5;
+    const long long warp_stride = (long long)gridDim.x * warps_per_block;
+    const int lane = threadIdx.x & 31;
+    for (long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < p.M; m += warp_stride) {
     int j = (int)(m % p.J);
     long long sf = m / p.J;
     int f = (int)(sf % p.F);
@@ -124,25 +151,89 @@ __global__ void embed_kernel(EmbedParams p) {
         in[2 + c] = v;
     }
     if (flip) in[2] = -in[2];
-    float* xo = p.x + (size_t)m * p.C;
-    const float* pos = p.spos + (size_t)j * p.C;
-    for (int c = lane; c < p.C; c += 32) {
-        const float* w = p.we + c * 5;
-        float acc = 0.f;
+    const int C = p.C;
+    float* xo = p.x + (size_t)m * C;
+    const float* pos = p.spos + (size_t)j * C;
+    float4 v[NV];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) acc = fmaf(in[i], w[i], acc);
-        acc += p.be[c];
-        acc += pos[c];
-        acc += p.temb[c];
-        xo[c] = acc;
+    for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C) {
+            float w[20];                                             // We[c .. c+3][0 .. 4], contiguous
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.we + (size_t)c * 5) + q);
+                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+            }
+            const float4 be = __ldg(reinterpret_cast<const float4*>(p.be + c));
+            const float4 po = __ldg(reinterpret_cast<const float4*>(pos + c));
+            const float4 te = __ldg(reinterpret_cast<const float4*>(p.temb + c));
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) acc = fmaf(in[q], w[5 * e + q], acc);
+                o[e] = acc;
+            }
+            v[i].x = ((o[0] + be.x) + po.x) + te.x;
+            v[i].y = ((o[1] + be.y) + po.y) + te.y;
+            v[i].z = ((o[2] + be.z) + po.z) + te.z;
+            v[i].w = ((o[3] + be.w) + po.w) + te.w;
+            *reinterpret_cast<float4*>(xo + c) = v[i];
+        }
     }
+    if (p.g1) {
+        float mean, rstd;
+        ln_row_stats<NV>(v, lane, C, mean, rstd, p.eps1);
+        op_t* oh = p.out_hi + (size_t)m * C;
+        op_t* ol = p.out_lo + (size_t)m * C;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = 4 * lane + 128 * i;
+            if (c < C) {
+                const float4 gg = __ldg(reinterpret_cast<const float4*>(p.g1 + c));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + c));
+                float y[4];
+                y[0] = (v[i].x - mean) * rstd * gg.x + bb.x;
+                y[1] = (v[i].y - mean) * rstd * gg.y + bb.y;
+                y[2] = (v[i].z - mean) * rstd * gg.z + bb.z;
+                y[3] = (v[i].w - mean) * rstd * gg.w + bb.w;
+                uint2 h, l;
+                split4(y, h, l);
+                *reinterpret_cast<uint2*>(oh + c) = h;
+                *reinterpret_cast<uint2*>(ol + c) = l;
+            }
+        }
+    }
+    }
+}
+
+// rows-per-warp kernels: exactly as many blocks as are resident at once (occupancy x SMs), each warp striding over rows
+// -- a larger grid would run its last blocks after the first ones have finished their whole stride loop
+template <typename K>
+static unsigned persistent_blocks(long long rows, int wpb, K kern) {
+    static int cached[MAX_DEVICES] = {0};                            // per kernel instance (template) and device
+    int& per_sm = cached[current_device_slot()];
+    if (per_sm == 0 &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, 0) != cudaSuccess || per_sm < 1))
+        per_sm = 4;
+    const long long want = (rows + wpb - 1) / wpb, cap = (long long)device_sm_count() * per_sm;
+    return (unsigned)(want < cap ? want : cap);
 }
 
 int launch_embed(const EmbedParams& p, cudaStream_t st) {
     if (p.M == 0) return 0;
+    if (p.C % 4 != 0 || p.C > 384) {
+        set_last_error("embed: C=%d unsupported (multiple of 4, <= 384)", p.C);
+        return -1;
+    }
     const int wpb = 8;
-    long long blocks = (p.M + wpb - 1) / wpb;
-    PAFUSE_CUDA_OK(launch_chain(embed_kernel, dim3((unsigned)blocks), dim3(wpb * 32), 0, st, 1, p));
+    if (p.C <= 256)
+        PAFUSE_CUDA_OK(launch_chain(embed_kernel<2>, dim3(persistent_blocks(p.M, wpb, embed_kernel<2>)), dim3(wpb * 32), 0, st, 1, p));
+    else
+        PAFUSE_CUDA_OK(launch_chain(embed_kernel<3>, dim3(persistent_blocks(p.M, wpb, embed_kernel<3>)), dim3(wpb * 32), 0, st, 1, p));
     PAFUSE_LAUNCH_OK();
     return 0;
 }
@@ -154,24 +245,6 @@ int launch_embed(const EmbedParams& p, cudaStream_t st) {
 // Second stage (g1 != nullptr):         a  = LN(x; g1,b1,eps1) -> fp16 hi/lo     (norm1 / norm2 of the next GEMM)
 // One warp per row, row kept in registers as NV float4 per lane (channels 4*lane + 128*i): 16-byte loads
 // and stores of x, 8-byte stores of the fp16 halves.
-template <int NV>
-__device__ __forceinline__ void ln_row_stats(const float4 (&v)[NV], int lane, int C, float& mean, float& rstd, float eps) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);   // lanes past C hold zeros
-    const float invC = 1.0f / (float)C;
-    mean = warp_sum(s) * invC;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        if (4 * lane + 128 * i < C) {
-            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
-        }
-    }
-    rstd = 1.0f / sqrtf(warp_sum(q) * invC + eps);
-}
-
 template <int NV>
 __global__ void __launch_bounds__(256) ln_chain_kernel(LnParams p) {
     pdl_launch_dependents();
@@ -261,54 +334,55 @@ int launch_ln_chain(const LnParams& p, cudaStream_t st) {
 // y = Linear(C,3)( LN_head( LN_shared(x) ) )      (mixste.py:273, :207-210, :291)
 // written straight into the whole-body prediction tensor [S,F,num_kps,3] at the
 // part's joint ids (replaces torch.cat, diffusionpose.py:165-171).
-template <int MAXV>
-__global__ void head_kernel(HeadParams p) {
+// One warp per row, the row in registers as NV float4 per lane (16-byte loads; the round-1 kernel read x with scalar
+// loads at 1.8-2.2 TB/s).
+template <int NV>
+__global__ void __launch_bounds__(256) head_kernel(HeadParams p) {
     pdl_launch_dependents();
     pdl_wait();
-    int warps_per_block = blockDim.x >> 5;
-    long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    if (m >= p.M) return;
-    int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long warp_stride = (long long)gridDim.x * warps_per_block;
+    const int lane = threadIdx.x & 31;
     const int C = p.C;
+    for (long long m = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < p.M; m += warp_stride) {
     const float* xr = p.x + (size_t)m * C;
-    float v[MAXV];
+    float4 v[NV];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        int c = lane + 32 * i;
-        v[i] = c < C ? xr[c] : 0.f;
+    for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        v[i] = c < C ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float invC = 1.0f / (float)C;
 #pragma unroll
     for (int stage = 0; stage < 2; ++stage) {
         const float* g = stage == 0 ? p.g0 : p.g1;
         const float* bb = stage == 0 ? p.b0 : p.b1;
-        float eps = stage == 0 ? p.eps0 : p.eps1;
+        const float eps = stage == 0 ? p.eps0 : p.eps1;
         if (!g) continue;
-        float s = 0.f;
+        float mean, rstd;
+        ln_row_stats<NV>(v, lane, C, mean, rstd, eps);
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) s += v[i];
-        float mean = warp_sum(s) * invC;
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            int c = lane + 32 * i;
-            float d = c < C ? v[i] - mean : 0.f;
-            q += d * d;
-        }
-        float rstd = (1.0f / sqrtf(warp_sum(q) * invC + eps));
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            int c = lane + 32 * i;
-            if (c < C) v[i] = (v[i] - mean) * rstd * g[c] + bb[c];
+        for (int i = 0; i < NV; ++i) {
+            const int c = 4 * lane + 128 * i;
+            if (c < C) {
+                const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bb + c));
+                v[i].x = (v[i].x - mean) * rstd * gg.x + b4.x;
+                v[i].y = (v[i].y - mean) * rstd * gg.y + b4.y;
+                v[i].z = (v[i].z - mean) * rstd * gg.z + b4.z;
+                v[i].w = (v[i].w - mean) * rstd * gg.w + b4.w;
+            }
         }
     }
     float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        int c = lane + 32 * i;
+    for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
         if (c < C) {
 #pragma unroll
-            for (int o = 0; o < 3; ++o) acc[o] = fmaf(v[i], p.wh[o * C + c], acc[o]);
+            for (int o = 0; o < 3; ++o) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(p.wh + (size_t)o * C + c));
+                acc[o] = fmaf(v[i].x, w.x, fmaf(v[i].y, w.y, fmaf(v[i].z, w.z, fmaf(v[i].w, w.w, acc[o]))));
+            }
         }
     }
 #pragma unroll
@@ -320,20 +394,20 @@ __global__ void head_kernel(HeadParams p) {
         float y = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : acc[2]) + p.bh[lane];
         p.pred[((size_t)sf * p.num_kps + g) * 3 + lane] = y;
     }
+    }
 }
 
 int launch_head(const HeadParams& p, cudaStream_t st) {
     if (p.M == 0) return 0;
     const int wpb = 8;
-    unsigned blocks = (unsigned)((p.M + wpb - 1) / wpb);
-    if (p.C <= 256)
-        PAFUSE_CUDA_OK(launch_chain(head_kernel<8>, dim3(blocks), dim3(wpb * 32), 0, st, 1, p));
-    else if (p.C <= 384)
-        PAFUSE_CUDA_OK(launch_chain(head_kernel<12>, dim3(blocks), dim3(wpb * 32), 0, st, 1, p));
-    else {
-        set_last_error("head: C=%d > 384 unsupported", p.C);
+    if (p.C % 4 != 0 || p.C > 384) {
+        set_last_error("head: C=%d unsupported (multiple of 4, <= 384)", p.C);
         return -1;
     }
+    if (p.C <= 256)
+        PAFUSE_CUDA_OK(launch_chain(head_kernel<2>, dim3(persistent_blocks(p.M, wpb, head_kernel<2>)), dim3(wpb * 32), 0, st, 1, p));
+    else
+        PAFUSE_CUDA_OK(launch_chain(head_kernel<3>, dim3(persistent_blocks(p.M, wpb, head_kernel<3>)), dim3(wpb * 32), 0, st, 1, p));
     PAFUSE_LAUNCH_OK();
     return 0;
 }

@@ -13,7 +13,7 @@
 // issues cta_group::2 MMAs that read both shared memories and write both tensor
 // memories.  Per byte fetched from L2 the pair does twice the math of a lone CTA --
 // the 1-CTA version of this kernel was L2->SMEM bound at 42 % tensor utilisation
-// (profiles/r1_gemm_1cta.txt).
+// (profiles/r1a_gemm_1cta_bf16x3_ncu_full.txt).
 //   warp 0    TMA producer: 4 tiled loads per stage (A_hi, A_lo, W_hi, W_lo; 128B swizzle)
 //   warp 1    MMA issuer (even CTA only): 3 x (BK/16) tcgen05.mma per stage, commits to mbarriers
 //   warp 2    TMEM allocator (512 columns = two BN<=256 accumulator buffers)
@@ -1069,7 +1069,7 @@ int make_map_planes(CUtensorMap* map, const void* ptr, long long rows_cap, int h
 
 int g_force_cg = 0;      // PAFUSE_GEMM_CTA_GROUP=1|2 overrides the default (2)
 int g_wres_enabled = 1;  // PAFUSE_GEMM_WRES=0 disables the weight-stationary mode
-int g_wres_min_stages = 4;  // with 3 stages (C = 384) the resident mode was slower than streaming (profiles/r1g_*)
+int g_wres_min_stages = 4;  // with 3 stages (C = 384) the resident mode was slower than streaming (round-1 session measurement, 2-3 % on the body GEMMs; no capture kept)
 
 template <int EPI, int CG, bool WRES>
 int launch_epi(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,

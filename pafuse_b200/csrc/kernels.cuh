@@ -22,6 +22,10 @@ struct EmbedParams {
     const float* spos;        // [J,C]
     const float* temb;        // [C]
     float* x;                 // [M,C] out
+    // optional: norm1 of STE block 0 applied to the row in the same pass -> fp16 hi/lo (nullptr: embedding only)
+    const float *g1 = nullptr, *b1 = nullptr;
+    float eps1 = 1e-6f;
+    op_t *out_hi = nullptr, *out_lo = nullptr;
 };
 
 struct LnParams {

@@ -312,8 +312,11 @@ int run_part(pafuse_ctx* ctx, int pi, Workspace& w, const float* x2d, const floa
     e.part_joints = p.joints_dev; e.flip_perm = ctx->flip_perm_dev;
     e.we = p.w("Spatial_patch_to_embedding.weight"); e.be = p.w("Spatial_patch_to_embedding.bias");
     e.spos = p.w("Spatial_pos_embed"); e.temb = p.temb; e.x = w.x;
+    // norm1 of STE block 0 rides on the embedding kernel (the row is in registers there)
+    e.g1 = p.w("STEblocks.0.norm1.weight"); e.b1 = p.w("STEblocks.0.norm1.bias"); e.eps1 = 1e-6f;
+    e.out_hi = w.a_hi; e.out_lo = w.a_lo;
     {
-        ProfScope ps(ctx, CAT_EMBED_HEAD, 4.0 * (double)M * C, st);
+        ProfScope ps(ctx, CAT_EMBED_HEAD, 8.0 * (double)M * C, st);
         if (int rc = launch_embed(e, st)) return rc;
     }
 
@@ -328,7 +331,7 @@ int run_part(pafuse_ctx* ctx, int pi, Workspace& w, const float* x2d, const floa
         l.M = M; l.C = C; l.J = J; l.F = F; l.x = w.x;
         l.g0 = l.b0 = nullptr; l.add_f = nullptr; l.eps0 = 1e-6f; l.eps1 = 1e-6f;
         l.out_hi = w.a_hi; l.out_lo = w.a_lo;
-        if (!fuse || blk == 0) {
+        if (!fuse && blk > 0) {
             // shared norm of the previous block (+ Temporal_pos_embed before TTE 0), then norm1 -> hi/lo
             if (blk > 0) {
                 const char* sn = temporal ? "Spatial_norm" : "Temporal_norm";   // norm that closed the previous block
