@@ -9,7 +9,12 @@ steps, flip-TTA) -> wb_pose_from_parts -> J-Agg / P-Agg.  Workload = BASELINE.js
 per GPU; with N GPUs every rank lifts its own 64 clips (clip sharding, weak scaling) and the
 aggregated poses are all-gathered over NCCL inside the step.  Random-init weights, synthetic 2D.
 
-Prints ONE JSON line on rank 0 (see README / DESIGN.md "Measurement" for the keys).
+Prints ONE JSON line on rank 0 (see README / DESIGN.md "Measurement" for the keys).  Beyond the contract keys:
+`parity_check` (GPU result vs the CPU oracle on the CPU sample's clips, at the benchmarked shape), `gpu_eager_baseline`
+(the same algorithm as eager fp32 PyTorch CUDA ops on this GPU), `sharding_check` (N > 1: rank 0 recomputes another
+rank's shard and compares bit for bit), `extra.cfg3` / `extra.cfg4` (N > 1 or --extra: BASELINE configs[2] hypothesis-
+sharded and configs[3] 512 clips per GPU, inside the same process), `roofline.issued_frac` (3 x frac: the tensor work
+the f16x3 format actually issues against the same peak).
 """
 from __future__ import annotations
 
@@ -341,6 +346,7 @@ def run_ours(args):
             "ms_per_step_profiled": ms_profiled,
             "share_of_step": g_ms / step_total_ms if step_total_ms else None,
             "launches": g_n,
+            "passes": 3, "issued_frac": 3.0 * gemm_tflops / tensor_peak,
             "path_tflops": fps / world * flops_per_frame(H, K) / 1e12,
             "path_frac": fps / world * flops_per_frame(H, K) / 1e12 / tensor_peak,
         },

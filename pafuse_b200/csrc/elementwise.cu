@@ -212,9 +212,10 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
 
 // rows-per-warp kernels: exactly as many blocks as are resident at once (occupancy x SMs), each warp striding over rows
 // -- a larger grid would run its last blocks after the first ones have finished their whole stride loop
-template <typename K>
-static unsigned persistent_blocks(long long rows, int wpb, K kern) {
-    static int cached[MAX_DEVICES] = {0};                            // per kernel instance (template) and device
+template <auto KERN>
+static unsigned persistent_blocks(long long rows, int wpb) {
+    auto kern = KERN;
+    static int cached[MAX_DEVICES] = {0};                            // per kernel instance (non-type template argument) and device
     int& per_sm = cached[current_device_slot()];
     if (per_sm == 0 &&
         (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, 0) != cudaSuccess || per_sm < 1))
@@ -231,9 +232,9 @@ int launch_embed(const EmbedParams& p, cudaStream_t st) {
     }
     const int wpb = 8;
     if (p.C <= 256)
-        PAFUSE_CUDA_OK(launch_chain(embed_kernel<2>, dim3(persistent_blocks(p.M, wpb, embed_kernel<2>)), dim3(wpb * 32), 0, st, 1, p));
+        PAFUSE_CUDA_OK(launch_chain(embed_kernel<2>, dim3(persistent_blocks<embed_kernel<2>>(p.M, wpb)), dim3(wpb * 32), 0, st, 1, p));
     else
-        PAFUSE_CUDA_OK(launch_chain(embed_kernel<3>, dim3(persistent_blocks(p.M, wpb, embed_kernel<3>)), dim3(wpb * 32), 0, st, 1, p));
+        PAFUSE_CUDA_OK(launch_chain(embed_kernel<3>, dim3(persistent_blocks<embed_kernel<3>>(p.M, wpb)), dim3(wpb * 32), 0, st, 1, p));
     PAFUSE_LAUNCH_OK();
     return 0;
 }
@@ -405,9 +406,9 @@ int launch_head(const HeadParams& p, cudaStream_t st) {
         return -1;
     }
     if (p.C <= 256)
-        PAFUSE_CUDA_OK(launch_chain(head_kernel<2>, dim3(persistent_blocks(p.M, wpb, head_kernel<2>)), dim3(wpb * 32), 0, st, 1, p));
+        PAFUSE_CUDA_OK(launch_chain(head_kernel<2>, dim3(persistent_blocks<head_kernel<2>>(p.M, wpb)), dim3(wpb * 32), 0, st, 1, p));
     else
-        PAFUSE_CUDA_OK(launch_chain(head_kernel<3>, dim3(persistent_blocks(p.M, wpb, head_kernel<3>)), dim3(wpb * 32), 0, st, 1, p));
+        PAFUSE_CUDA_OK(launch_chain(head_kernel<3>, dim3(persistent_blocks<head_kernel<3>>(p.M, wpb)), dim3(wpb * 32), 0, st, 1, p));
     PAFUSE_LAUNCH_OK();
     return 0;
 }

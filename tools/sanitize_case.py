@@ -31,6 +31,14 @@ def main():
     traj, cam = synthetic.synthetic_trajectory(x2d.shape[0], seed=1).cuda(), synthetic.h36m_cam0_intrinsics().cuda()
     jagg, pagg, sel = pafuse_b200.aggregate_hypotheses(wb, traj, cam, x2d, return_select=True)
     m = loss.evaluate_metrics(wb, jagg[:, -1], traj, cam, x2d)
+    # round-2 entry points: part-based metrics, counter-based noise, graph replay of a small pass (second / third forward)
+    loss.mpjpe_diffusion(wb, jagg[:, -1], part_based=True, dataset=sk)
+    loss.mpjpe_diffusion_all_min(wb, jagg[:, -1], mean_pos=True, part_based=True, dataset=sk)
+    model.native_context().randn(1, 0, 3, 2, 1001, 4000)
+    noises = [torch.randn(x2d.shape[0], H, 27, 134, 3, device="cuda") for _ in range(K)]
+    model.noise_source = lambda k, shape, device: noises[k]
+    for _ in range(3):
+        pred2 = model(x2d, None, input_2d_flip=x2df)
     torch.cuda.synchronize()
     print("sanitize case ok", tuple(res["prediction"].shape), float(pagg.abs().mean()), {k: float(v[-1]) for k, v in m.items()})
 
