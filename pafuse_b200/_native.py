@@ -77,7 +77,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library; PAFUSE_LIB names another build of the same sources for A/B measurements."""
+    return os.environ.get("PAFUSE_LIB") or _build.LIB_PATH
 
 
 def load_library(build_if_missing: bool = True):
@@ -86,7 +87,7 @@ def load_library(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if build_if_missing and _build.needs_build():
+    if build_if_missing and path == _build.LIB_PATH and _build.needs_build():
         try:
             _build.build()
         except Exception as e:  # no nvcc on the box and a stale/missing .so

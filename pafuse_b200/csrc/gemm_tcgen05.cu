@@ -53,7 +53,10 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_SLACK = 1024;
 constexpr int SMEM_SLACK_LN = 3072;
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_WARPS = 16;
+#ifndef PAFUSE_EPI_WARPS
+#define PAFUSE_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = PAFUSE_EPI_WARPS;         // 16 (default) or 8 (A/B builds: -DPAFUSE_EPI_WARPS=8)
 constexpr int EPI_SUBS = EPI_WARPS / 4;             // epilogue warps per TMEM lane quarter
 constexpr int NUM_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // 640
 constexpr int CW = 16;                              // accumulator columns per epilogue chunk
@@ -61,8 +64,13 @@ constexpr int TMEM_COLS = 512;
 constexpr int STG_WARP_BYTES = 2048;                // per epilogue warp: one staging box of 32 rows x 64 B (fp32) or hi + lo boxes of 32 rows x 32 B
 constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 // register budget (setmaxnreg, per thread): 4 control warps x 32 x 64 + 16 epilogue warps x 32 x 104 = 61440 <= 65536
+#if PAFUSE_EPI_WARPS == 16
 #define PAFUSE_REGS_CTRL "64"
 #define PAFUSE_REGS_EPI "104"
+#else                                               // 384 threads x 168: 4 x 32 x 64 + 8 x 32 x 216 = 63488 <= 64512
+#define PAFUSE_REGS_CTRL "64"
+#define PAFUSE_REGS_EPI "216"
+#endif
 
 struct KernelParams {
     long long M;
@@ -140,7 +148,7 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t r[8]
 }
 __device__ __forceinline__ void tmem_st_wait_all() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // the EPI_SUBS warps that share a TMEM lane quarter (128 threads), barrier id 1 + quarter
-__device__ __forceinline__ void quarter_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void quarter_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(EPI_SUBS * 32) : "memory"); }
 // staging-box offsets of 16-byte piece i of row `row`: fp32 boxes are 32 rows x 64 B with the 64-byte swizzle
 // (piece i at i ^ ((row >> 1) & 3)), fp16 boxes 32 rows x 32 B with the 32-byte swizzle (piece i at i ^ ((row >> 2) & 1));
 // both patterns are bank-conflict free for a quarter-warp of consecutive rows

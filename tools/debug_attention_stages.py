@@ -1,3 +1,9 @@
+"""Attention kernel at unit counts that make every CTA re-use its ring slots many times (S = 40 sequences: 18-37 units
+per CTA), against fp64 torch -- the case that exposed the slot-sharing hazard of the three-stage variant
+(PAFUSE_ATT_STAGES=3).
+
+    CUDA_LAUNCH_BLOCKING=1 [PAFUSE_ATT_STAGES=3] python tools/debug_attention_stages.py
+"""
 import sys, torch
 sys.path.insert(0, '.')
 from pafuse_b200 import _native
