@@ -77,6 +77,9 @@ struct AttnTcParams {
     int n_acc;                // O accumulators per stage (HDP columns each): the three f16x3 passes of PV go to different ones
     op_t* o_hi;
     op_t* o_lo;
+#ifdef PAFUSE_ABLATE
+    int ablate;               // energy ablation builds only (tools/energy_ablation.py): 4 = softmax / output warps skip their work, 8 = no MMAs
+#endif
 };
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
@@ -299,6 +302,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 // before this point and the tensor pipe executes in issue order
 #pragma unroll
                 for (int k = 0; k < HDP / 16; ++k) {
+#ifdef PAFUSE_ABLATE
+                    if (p.ablate & 8) break;
+#endif
                     const uint64_t ko = (uint64_t)(k * 2);     // 32 bytes along the row, in 16-byte descriptor units
                     umma_f16_ss<1>(d_s, ql0 + so + ko, kh0 + so + ko, idesc_qk, k != 0 ? 1u : 0u);
                     umma_f16_ss<1>(d_s, qh0 + so + ko, kl0 + so + ko, idesc_qk, 1u);
@@ -319,6 +325,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 uint64_t vh = vh0 + slot_off(it), vl = vl0 + slot_off(it);
                 uint32_t ph_a = d_phi, pl_a = d_plo;
                 for (int k = 0; k < key_steps; ++k, vh += V_STEP, vl += V_STEP, ph_a += 8u, pl_a += 8u) {
+#ifdef PAFUSE_ABLATE
+                    if (p.ablate & 8) break;
+#endif
                     // 16 keys further down the V tile / 16 fp16 keys = 8 tensor-memory columns further in P
                     // Separate accumulators per pass: the PV MMAs are tiny (N = HDP) and a chain of 3 * key_steps
                     // dependent accumulations into ONE tile ran at the pipe's latency, ~90 cycles per MMA
@@ -381,6 +390,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             mbar_wait(&s_full[wg], ph);
             tcgen05_fence_after();
             float sum = 0.f;
+#ifdef PAFUSE_ABLATE
+            if (p.ablate & 4) {                                // same barrier protocol, no loads / math / stores
+                if (SEP) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_empty[wg]);
+                    if (warp_live && it >= NSTG) mbar_wait(&o_full[wg], (uint32_t)((it - NSTG) / NSTG) & 1u);
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[wg]);
+                return 1.f;
+            }
+#endif
             uint32_t sv[NCH_MAX * 32];
             if (warp_live) {
                 // the scores of this row against the keys of its group, once, into registers
@@ -450,6 +473,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             const int tile = u >> 3, head = u & 7;
             mbar_wait(&o_full[wg], ph);
             tcgen05_fence_after();
+#ifdef PAFUSE_ABLATE
+            if (p.ablate & 4) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&o_empty[wg]);
+                return;
+            }
+#endif
             uint32_t ov[HDP];
             if (warp_live) {
                 tmem_ld_32x32(o_addr, ov);
@@ -699,6 +730,9 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
         }
     }
     if (p.n_acc > g_n_acc_cap) p.n_acc = g_n_acc_cap < 1 ? 1 : g_n_acc_cap;
+#ifdef PAFUSE_ABLATE
+    p.ablate = getenv("PAFUSE_ABLATE") ? atoi(getenv("PAFUSE_ABLATE")) : 0;
+#endif
     p.hd = hd;
     p.C = C;
     p.J = J;

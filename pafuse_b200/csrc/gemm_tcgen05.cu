@@ -86,6 +86,9 @@ struct KernelParams {
     const float* bias;
     int hds;                         // EPI_PLANES: stored head width (columns per plane, a multiple of 16)
     GemmLnFuse ln;                   // EPI_RESID_LN
+#ifdef PAFUSE_ABLATE
+    int ablate;                      // energy ablation builds only (tools/energy_ablation.py): 1 = epilogue warps skip their work, 2 = no MMAs
+#endif
 };
 
 // Tile walk of one CTA group.  Streaming mode: tiles (m, n) in m-major order, strided over the groups, so
@@ -571,6 +574,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                     }
                     int k_left = p.K - kb * a_bk;
                     int nk = k_left >= a_bk ? a_bk / UK : (k_left + UK - 1) / UK;   // K tail: TMA zero-fills, skip dead slices
+#ifdef PAFUSE_ABLATE
+                    if (p.ablate & 2) nk = 0;                         // operands still travel, barriers still cycle
+#endif
                     for (int k = 0; k < nk; ++k) {
                         const uint32_t koff = (uint32_t)k * UK * 2;   // bytes along K inside the swizzle span
                         const uint64_t dah = make_smem_desc(a_hi + koff, a_sbo, a_layout);
@@ -617,6 +623,16 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             walk.at(it, m_tile, n_tile);
             const int row0 = (m_tile * CG + (int)cta_rank) * BM + q * 32;   // first row of this warp's box
             float4 xr[4];                                             // EPI_RESID_LN: x of the next chunk
+#ifdef PAFUSE_ABLATE
+            if (p.ablate & 1) {                                       // accumulator handed straight back: no loads, math, stores
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tcgen05_fence_after();
+                release(&tmem_empty_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                continue;
+            }
+#endif
             if (EPI == EPI_RESID_LN) {
                 if (sub < nck) ln_fetch_x(p, xr, row0, sub * CW, lane);   // in flight while the main loop finishes
             }
@@ -1129,6 +1145,9 @@ int launch_cg(const GemmArgs& g, cudaStream_t st) {
     kp.bias = g.bias;
     kp.hds = g.planes.hds;
     kp.ln = g.ln;
+#ifdef PAFUSE_ABLATE
+    kp.ablate = getenv("PAFUSE_ABLATE") ? atoi(getenv("PAFUSE_ABLATE")) : 0;
+#endif
     if (g.epilogue == EPI_RESID_LN) {
         if (!gemm_can_fuse_ln(g.N) || kp.n_tiles != 1 || !g.ln.x || g.ln.x != g.out_f32 || !g.ln.g1 || !g.ln.b1 ||
             !g.out_hi || !g.out_lo || (g.ln.g0 && !g.ln.b0)) {
