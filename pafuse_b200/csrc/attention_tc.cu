@@ -42,14 +42,12 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include <type_traits>
-
 namespace pafuse {
 
 namespace {
 
 constexpr int TILE_ROWS = 128;
-__host__ __device__ constexpr int att_threads(int nstg, int split) { return nstg == 2 && split == 1 ? 384 : 640; }
+__host__ __device__ constexpr int att_threads(int nstg) { return nstg == 2 ? 384 : 640; }
 // TMEM columns, two layouts (AttnTcParams::tm_*):
 //   aliased (SEP = false): stage s holds S (fp32, 128 columns) at s*128, overwritten in place by P_hi (64 columns
 //     of packed fp16 pairs) and P_lo (next 64); O (fp32, HDP columns) at 256 + s*64.  QK^T of unit i+2 can only
@@ -71,9 +69,9 @@ struct AttnTcParams {
     float scale_log2e;        // hd^-0.5 * log2(e)
     int stg_pitch;            // output staging: bytes between rows (= 2*hd + 16)
     int stg_warp_bytes;       // 32 staging rows, rounded up to 128 B
-    int chunk_bytes;          // 16, or 8 when a head slice (or a warp's part of it) is not 16-byte aligned in [token, C]
-    int cp_chunks[2];         // chunks of a staging row, per warp of a split slice ([0] alone without the split)
-    int cp_rows[2];           // 32 / cp_chunks: staging rows one copy-out instruction of a warp covers
+    int chunk_bytes;          // 16, or 8 when a head slice is not 16-byte aligned in [token, C]
+    int chunks_per_row;       // 2*hd / chunk_bytes
+    int rows_per_iter;        // 32 / chunks_per_row: staging rows one copy-out instruction of a warp covers
     // tensor-memory columns: S / P of stage s at tm_s0 + s * tm_stride_s (+ tm_phi_off / tm_plo_off), O at tm_o0 + s * tm_stride_o
     int tm_s0, tm_stride_s, tm_phi_off, tm_plo_off, tm_o0, tm_stride_o;
     int n_acc;                // O accumulators per stage (HDP columns each): the three f16x3 passes of PV go to different ones
@@ -113,20 +111,6 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t r[1
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
           "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t r[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t r[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -177,10 +161,9 @@ __device__ __forceinline__ void split_pair2(float2 v, uint32_t& hi, uint32_t& lo
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// HDP: tile row width in fp16 elements (64 / 32).  LT: compile-time group length (0 = use p.L; NCH_MAX chunks).
-// SPLIT: softmax warps per 32-row slice of the tile (1, or 2 with NSTG == 2: 16 softmax warps, 640 threads)
-template <int HDP, int LT, bool SEP, int NSTG, int SPLIT>
-__global__ void __launch_bounds__(att_threads(NSTG, SPLIT), 1)
+// HDP: tile row width in fp16 elements (64 / 32).  LT: compile-time group length (0 = use p.L; NCH_MAX chunks)
+template <int HDP, int LT, bool SEP, int NSTG>
+__global__ void __launch_bounds__(att_threads(NSTG), 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                     const AttnTcParams p) {
     constexpr int ROWB = HDP * 2;                              // bytes per tile row = swizzle span
@@ -200,9 +183,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     __shared__ __align__(8) uint64_t qk_full[NS], qk_empty[NS], v_full[NS], v_empty[NS];
     __shared__ __align__(8) uint64_t s_full[NSTG], s_empty[NSTG], p_full[NSTG];
     __shared__ __align__(8) uint64_t o_full[NSTG * 2], o_empty[NSTG * 2];      // [stage * 2 + O buffer]
-    constexpr int ATT_THREADS = att_threads(NSTG, SPLIT);
-    // split slices: row maxima [0] and row sums [1] of the two warps of a slice, per stage
-    __shared__ float xch_buf[SPLIT == 2 ? NSTG : 1][2][2][SPLIT == 2 ? TILE_ROWS : 1];
+    constexpr int ATT_THREADS = att_threads(NSTG);
     constexpr int CTRL_WARPS = NSTG == 2 ? 4 : 8;              // warps before the softmax groups (whole warpgroups)
     __shared__ uint32_t tmem_base_slot;
 
@@ -241,11 +222,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         }
         for (int s = 0; s < NSTG; ++s) {
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], n_live * SPLIT);
-            mbar_init(&p_full[s], n_live * SPLIT);             // one lane per live warp of the stage's softmax group
+            mbar_init(&s_empty[s], n_live);
+            mbar_init(&p_full[s], n_live);                     // one lane per live warp of the stage's softmax group
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&o_full[s * 2 + b], 1);
-                mbar_init(&o_empty[s * 2 + b], n_live * SPLIT);
+                mbar_init(&o_empty[s * 2 + b], n_live);
             }
         }
         fence_barrier_init();
@@ -265,8 +246,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     const bool is_issuer = NSTG == 2 ? (warp == 1 || warp == 2) : (warp >= 3 && warp < 6);
     const int ctrl_stage = NSTG == 2 ? (warp == 0 ? 0 : warp == 3 ? 1 : warp - 1) : warp % 3;
     if (warp < CTRL_WARPS) {
-    if (NSTG == 2 && SPLIT == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");    // control warpgroup(s) donate registers ...
-    else if (NSTG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (NSTG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");    // control warpgroup(s) donate registers ...
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (is_producer) {
         // ===================== TMA producers: warp 0 feeds ring stage 0 (units 0, 2, ...), warp 3 stage 1 ==========
@@ -390,17 +370,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         }
     }
     } else {
-        if (NSTG == 2 && SPLIT == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");   // ... to the softmax warpgroups
-        else if (NSTG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");             // 4*32*56 + 16*32*104 = 60416 <= 640*96
+        if (NSTG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");   // ... to the softmax warpgroups
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");             // 8*32*40 + 12*32*128 = 59392 <= 640*96 (the CTA's register allocation)
         // ===================== softmax + output =====================
-        // SPLIT warps share a 32-row slice of the tile (all of them may access its TMEM lane quarter): warp `half` of the
-        // slice takes columns [half*CW, half*CW + CW) of every 32-column score chunk and HQ of the HDP output columns.
-        constexpr int CW = 32 / SPLIT;                         // score columns of a chunk this warp owns
-        constexpr int HQ = HDP / SPLIT;                        // output columns this warp owns
         const int sw = warp - CTRL_WARPS;
-        const int wg = sw / (4 * SPLIT);                       // softmax group = TMEM stage
-        const int half = SPLIT == 2 ? (sw >> 2) & 1 : 0;
+        const int wg = sw >> 2;                                // softmax group = TMEM stage
         const int q = warp & 3;                                // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;                           // tile row == TMEM lane
         // all 32 rows of a warp belong to one group (Lp is a multiple of 32)
@@ -416,15 +390,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         const uint32_t stg_s = smem_u32(smem + NS * STAGE_BYTES + sw * p.stg_warp_bytes);  // this warp's output staging rows
         const uint32_t my_row_s = stg_s + (uint32_t)(lane * p.stg_pitch);
         const int n_zero_chunks = (key_steps + 1) / 2;         // 32-key chunks the PV product reads
-        const int cpr = p.cp_chunks[half], rpi = p.cp_rows[half];
+        const int cpr = p.chunks_per_row, rpi = p.rows_per_iter;
         const int cp_row = lane / cpr;                         // copy-out role of this lane
         const int cp_cc = lane - cp_row * cpr;
         const bool cp_active = cp_row < rpi;
-        const int live_cols = min(HQ, p.hd - half * HQ);       // output columns of this warp that exist (may be <= 0: nothing to store)
-        const int pair_bar = 1 + wg * 4 + q;                   // named barrier of the SPLIT warps of this slice
-        float* my_xch = &xch_buf[SPLIT == 2 ? wg : 0][0][half][SPLIT == 2 ? r : 0];          // + 2 * TILE_ROWS: the sum slots
-        float* peer_xch = &xch_buf[SPLIT == 2 ? wg : 0][0][half ^ 1][SPLIT == 2 ? r : 0];
-        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
 #ifdef PAFUSE_ATT_TRACE
         // measurement builds only: cycles per phase of the unit loop, printed by one warp of every softmax group of CTA 0
         long long tr[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tr_last = clock64();
@@ -433,9 +402,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 #define ATT_TR(i)
 #endif
 
-        // the whole unit loop is instantiated per `half` so that the column masks stay compile-time constants
-        auto group_loop = [&](auto HALF_C) {
-        constexpr int HALF = decltype(HALF_C)::value;
         // keys of the other groups: exact zeros in P.  The separate layout never overwrites them: once is enough.
         auto zero_other_groups = [&]() {
             uint32_t z[16];
@@ -443,8 +409,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             for (int i = 0; i < 16; ++i) z[i] = 0u;
             for (int c = 0; c < n_zero_chunks; ++c)
                 if (c < c0 || c >= c0 + nch) {
-                    if (SPLIT == 1 || HALF == 0) tmem_st_32x16(phi_addr + (uint32_t)(c * 16), z);
-                    if (SPLIT == 1 || HALF == 1) tmem_st_32x16(plo_addr + (uint32_t)(c * 16), z);
+                    tmem_st_32x16(phi_addr + (uint32_t)(c * 16), z);
+                    tmem_st_32x16(plo_addr + (uint32_t)(c * 16), z);
                 }
         };
         if (SEP && warp_live) {
@@ -474,15 +440,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 return 1.f;
             }
 #endif
-            uint32_t sv[NCH_MAX * CW];
+            uint32_t sv[NCH_MAX * 32];
             if (warp_live) {
                 // the scores of this row against the keys of its group (this warp's columns), once, into registers
 #pragma unroll
                 for (int k = 0; k < NCH_MAX; ++k)
-                    if (k < nch && (LT == 0 || k * 32 + HALF * CW < LT)) {
-                        if (SPLIT == 1) tmem_ld_32x32(s_addr + (uint32_t)((c0 + k) * 32), &sv[k * CW]);
-                        else tmem_ld_32x16(s_addr + (uint32_t)((c0 + k) * 32 + HALF * CW), &sv[k * CW]);
-                    }
+                    if (k < nch) tmem_ld_32x32(s_addr + (uint32_t)((c0 + k) * 32), &sv[k * 32]);
                 tmem_ld_wait();
             }
             ATT_TR(1)
@@ -498,16 +461,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 for (int k = 0; k < NCH_MAX; ++k)
                     if (k < nch) {
 #pragma unroll
-                        for (int i = 0; i < CW; ++i)
-                            if (k * 32 + HALF * CW + i < L) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[k * CW + i]));
+                        for (int i = 0; i < 32; ++i)
+                            if (k * 32 + i < L) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[k * 32 + i]));
                     }
-                float mrow = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                if (SPLIT == 2) {                              // the other warp of the slice holds the other columns of the row
-                    *my_xch = mrow;
-                    pair_sync();
-                    mrow = fmaxf(mrow, *peer_xch);
-                }
-                const float moff = mrow * sc;
+                const float moff = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sc;
                 ATT_TR(2)
                 // p = exp2(s*c - m*c), row sum, fp16 hi/lo -- on packed pairs (FFMA2 / FADD2, common.cuh): the softmax
                 // groups are bound by instruction issue and latency, not by the FMA pipe
@@ -516,13 +473,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < NCH_MAX; ++k)
                     if (k < nch) {
-                        uint32_t hi16[CW / 2], lo16[CW / 2];
+                        uint32_t hi16[16], lo16[16];
 #pragma unroll
-                        for (int i = 0; i < CW / 2; ++i) {
-                            const int col = k * 32 + HALF * CW + 2 * i;                 // compile-time masks for LT != 0
+                        for (int i = 0; i < 16; ++i) {
+                            const int col = k * 32 + 2 * i;                 // compile-time masks for LT != 0
                             float2 pr = make_float2(0.f, 0.f);
                             if (col < L) {
-                                pr = ffma2(make_float2(__uint_as_float(sv[k * CW + 2 * i]), __uint_as_float(sv[k * CW + 2 * i + 1])),
+                                pr = ffma2(make_float2(__uint_as_float(sv[k * 32 + 2 * i]), __uint_as_float(sv[k * 32 + 2 * i + 1])),
                                            sc2, nm2);
                                 pr.x = fast_exp2(pr.x);
                                 pr.y = col + 1 < L ? fast_exp2(pr.y) : 0.f;
@@ -539,23 +496,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                             tcgen05_fence_after();
                             ATT_TR(4)
                         }
-                        if (SPLIT == 1) {
-                            tmem_st_32x16(phi_addr + (uint32_t)((c0 + k) * 16), hi16);
-                            tmem_st_32x16(plo_addr + (uint32_t)((c0 + k) * 16), lo16);
-                        } else {
-                            tmem_st_32x8(phi_addr + (uint32_t)((c0 + k) * 16 + HALF * 8), hi16);
-                            tmem_st_32x8(plo_addr + (uint32_t)((c0 + k) * 16 + HALF * 8), lo16);
-                        }
+                        tmem_st_32x16(phi_addr + (uint32_t)((c0 + k) * 16), hi16);
+                        tmem_st_32x16(plo_addr + (uint32_t)((c0 + k) * 16), lo16);
                     }
                 sum = (s2[0].x + s2[0].y) + (s2[1].x + s2[1].y);
                 if (!SEP) ATT_TR(3)
-                if (SPLIT == 2) my_xch[2 * TILE_ROWS] = sum;   // separate slots: the peer may still be reading the maxima
                 if (!SEP) zero_other_groups();
                 tmem_st_wait();
-                if (SPLIT == 2) {
-                    pair_sync();
-                    sum += peer_xch[2 * TILE_ROWS];            // fp32 addition commutes: both warps get the same total
-                }
             }
             // rows of a dead warp feed stale bits into rows of O nobody stores: nothing to write for them
             tcgen05_fence_before();
@@ -583,25 +530,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 return;
             }
 #endif
-            uint32_t ov[HQ];
+            uint32_t ov[HDP];
             auto load_o = [&](uint32_t addr, uint32_t* dst) {
-                if (HQ == 64) {
-                    tmem_ld_32x32(addr, dst);
-                    tmem_ld_32x32(addr + 32u, dst + 32);
-                } else if (HQ == 32) {
-                    tmem_ld_32x32(addr, dst);
-                } else {
-                    tmem_ld_32x16(addr, dst);
-                }
+                tmem_ld_32x32(addr, dst);
+                if (HDP == 64) tmem_ld_32x32(addr + 32u, dst + 32);
             };
             if (warp_live) {
-                load_o(o_addr + ob_off + (uint32_t)(HALF * HQ), ov);
+                load_o(o_addr + ob_off, ov);
                 for (int a = 1; a < p.n_acc; ++a) {            // add the other passes' accumulators
-                    uint32_t oa[HQ];
-                    load_o(o_addr + ob_off + (uint32_t)(a * HDP + HALF * HQ), oa);
+                    uint32_t oa[HDP];
+                    load_o(o_addr + ob_off + (uint32_t)(a * HDP), oa);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < HQ / 2; ++i) {
+                    for (int i = 0; i < HDP / 2; ++i) {
                         const float2 t = fadd2(make_float2(__uint_as_float(ov[2 * i]), __uint_as_float(ov[2 * i + 1])),
                                                make_float2(__uint_as_float(oa[2 * i]), __uint_as_float(oa[2 * i + 1])));
                         ov[2 * i] = __float_as_uint(t.x);
@@ -614,7 +555,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_empty[wg * 2 + ob]);
             ATT_TR(7)
-            if (!warp_live || live_cols <= 0) return;
+            if (!warp_live) return;
             // token of staging row i of this warp = tok0 + i * tstride, for i < n_rows (all warp-uniform)
             long long tok0;
             int tstride, n_rows = min(32, L - row0_in_g);
@@ -636,15 +577,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             float inv;                                         // one MUFU instead of the IEEE division sequence: 1 ulp on a scale factor
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sum));
             const float2 inv2 = splat2(inv);
-            uint32_t oh[HQ / 2], ol[HQ / 2];
+            uint32_t oh[HDP / 2], ol[HDP / 2];
 #pragma unroll
-            for (int i = 0; i < HQ / 2; ++i)
+            for (int i = 0; i < HDP / 2; ++i)
                 split_pair2(fmul2(make_float2(__uint_as_float(ov[2 * i]), __uint_as_float(ov[2 * i + 1])), inv2), oh[i], ol[i]);
             // copy-out: lane -> (row lane / cpr of the current group of rows_per_iter rows, chunk lane % cpr); the
             // per-chunk index arithmetic of the first version (64-bit multiplies per 8 bytes) cost as many
             // instructions as the softmax itself (profiles/r1h_*)
             const size_t row_bytes = (size_t)tstride * (size_t)(p.C * 2);
-            const size_t dst0 = (size_t)tok0 * (size_t)(p.C * 2) + (size_t)(head * p.hd * 2 + HALF * HQ * 2 + cp_cc * p.chunk_bytes) +
+            const size_t dst0 = (size_t)tok0 * (size_t)(p.C * 2) + (size_t)(head * p.hd * 2 + cp_cc * p.chunk_bytes) +
                                 (size_t)cp_row * row_bytes;
             const size_t dst_step = (size_t)rpi * row_bytes;
             ATT_TR(8)
@@ -652,8 +593,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             for (int hl = 0; hl < 2; ++hl) {
                 __syncwarp();                                  // the previous copy-out has read the staging rows
 #pragma unroll
-                for (int i = 0; i < HQ / 4; ++i)
-                    if (4 * i < live_cols) {
+                for (int i = 0; i < HDP / 4; ++i)
+                    if (4 * i < p.hd) {
                         if (hl == 0) sts64(my_row_s + 8u * i, oh[2 * i], oh[2 * i + 1]);
                         else sts64(my_row_s + 8u * i, ol[2 * i], ol[2 * i + 1]);
                     }
@@ -718,14 +659,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             }
             if (prev >= 0) output_unit(prev, prev_sum);
         }
-        };   // group_loop
-        if (SPLIT == 1 || half == 0) group_loop(std::integral_constant<int, 0>{});
-        else group_loop(std::integral_constant<int, SPLIT - 1>{});
 #ifdef PAFUSE_ATT_TRACE
-        if (blockIdx.x == 0 && lane == 0 && q == 0 && half == 0 && n_local > 0)
-            printf("att_trace HDP=%d L=%d SEP=%d SPLIT=%d grp=%d units=%d cycles/unit: s_full_wait %lld | S_ld %lld | max %lld | exp_split %lld | "
+        if (blockIdx.x == 0 && lane == 0 && q == 0 && n_local > 0)
+            printf("att_trace HDP=%d L=%d SEP=%d grp=%d units=%d cycles/unit: s_full_wait %lld | S_ld %lld | max %lld | exp_split %lld | "
                    "o_full_wait(prev) %lld | P_st+arrive %lld | o_full_wait %lld | O_ld %lld | convert %lld | copyout %lld | other %lld\n",
-                   HDP, L, (int)SEP, SPLIT, wg, (n_local - wg + NSTG - 1) / NSTG, tr[0] * NSTG / n_local, tr[1] * NSTG / n_local, tr[2] * NSTG / n_local,
+                   HDP, L, (int)SEP, wg, (n_local - wg + NSTG - 1) / NSTG, tr[0] * NSTG / n_local, tr[1] * NSTG / n_local, tr[2] * NSTG / n_local,
                    tr[3] * NSTG / n_local, tr[4] * NSTG / n_local, tr[5] * NSTG / n_local, tr[6] * NSTG / n_local, tr[7] * NSTG / n_local,
                    tr[8] * NSTG / n_local, tr[10] * NSTG / n_local, tr[9] * NSTG / n_local);
 #endif
@@ -747,7 +685,6 @@ int g_stages = 2;        // PAFUSE_ATT_STAGES=3: three units in flight per SM wh
                          // kernel), so Q, K, V of unit i+3 are requested only when unit i has used them -- the two-stage kernel asks three units
                          // ahead, and that prefetch distance is worth more than the third unit in flight
 int g_pipe_o = 1;        // PAFUSE_ATT_PIPE=0: aliased layout without the second O buffer (the group waits for PV before it writes out)
-int g_split = 1;         // PAFUSE_ATT_SPLIT=2: two softmax warps per 32-row slice (narrow heads, two stages): 16 softmax warps per SM
 int g_sep_mode = 1;      // PAFUSE_ATT_SEP: 0 aliased layout only, 1 separate when it fits (default), 2 also with one group less per tile (slower: measured)
 
 int att_init() {
@@ -763,7 +700,6 @@ int att_init() {
     if (const char* e = getenv("PAFUSE_ATT_SEP")) g_sep_mode = atoi(e);
     if (const char* e = getenv("PAFUSE_ATT_NACC")) g_n_acc_cap = atoi(e);
     if (const char* e = getenv("PAFUSE_ATT_STAGES")) g_stages = atoi(e);
-    if (const char* e = getenv("PAFUSE_ATT_SPLIT")) g_split = atoi(e);
     if (const char* e = getenv("PAFUSE_ATT_PIPE")) g_pipe_o = atoi(e);
     return 0;
 }
@@ -800,15 +736,15 @@ int make_plane_map(CUtensorMap* map, const op_t* base, long long rows_cap, int h
     return 0;
 }
 
-template <int HDP, int LT, bool SEP, int NSTG, int SPLIT>
+template <int HDP, int LT, bool SEP, int NSTG>
 int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, cudaStream_t st, int sms) {
     constexpr int NS = NSTG == 3 ? 3 : (HDP == 32 ? 4 : 2);            // operand ring slots (see the kernel)
-    const int SMEM = NS * 6 * TILE_ROWS * HDP * 2 + 4 * NSTG * SPLIT * p.stg_warp_bytes + 1024;
+    const int SMEM = NS * 6 * TILE_ROWS * HDP * 2 + 4 * NSTG * p.stg_warp_bytes + 1024;
     if (SMEM > 227 * 1024) {
         set_last_error("attention_tc: head_dim %d needs %d bytes of shared memory", p.hd, SMEM);
         return -1;
     }
-    auto kern = attention_tc_kernel<HDP, LT, SEP, NSTG, SPLIT>;
+    auto kern = attention_tc_kernel<HDP, LT, SEP, NSTG>;
     static int configured[MAX_DEVICES] = {0};                          // per template instance and per device
     const int dev = current_device_slot();
     if (configured[dev] < SMEM) {
@@ -820,7 +756,7 @@ int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& 
     // on an SM share the CTAs are placed as pairs (no cluster feature is used), so that the share keeps whole
     // TPCs and the CTA pairs of the GEMMs running next to it on other streams still find two free SMs together
     const int cluster = sms < device_sm_count() && grid % 2 == 0 ? 2 : 1;
-    PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(att_threads(NSTG, SPLIT)), (size_t)SMEM, st, cluster, mh, ml, p));
+    PAFUSE_CUDA_OK(launch_chain(kern, dim3((unsigned)grid), dim3(att_threads(NSTG)), (size_t)SMEM, st, cluster, mh, ml, p));
     PAFUSE_LAUNCH_OK();
     return 0;
 }
@@ -908,33 +844,20 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
     p.scale_log2e = (float)(pow((double)hd, -0.5) * 1.4426950408889634);
     p.o_hi = o_hi;
     p.o_lo = o_lo;
-    const bool split = hdp == 32 && !three && g_split >= 2;   // the wide heads have no shared memory left for 16 staging areas
-    p.chunk_bytes = (2 * hd) % 16 == 0 ? 16 : 8;              // hd % 4 == 0, so a slice is at least 8-byte aligned
-    if (!split) {
-        p.stg_pitch = 2 * hd + 16;
-        p.cp_chunks[0] = p.cp_chunks[1] = 2 * hd / p.chunk_bytes;
-    } else {
-        const int hq = hdp / 2;                               // output columns per warp of a slice: [0, hq) and [hq, hd)
-        p.stg_pitch = 2 * hq + 16;
-        p.cp_chunks[0] = 2 * (hd < hq ? hd : hq) / p.chunk_bytes;
-        p.cp_chunks[1] = hd > hq ? 2 * (hd - hq) / p.chunk_bytes : 1;
-    }
-    p.cp_rows[0] = 32 / p.cp_chunks[0];
-    p.cp_rows[1] = 32 / p.cp_chunks[1];
+    p.stg_pitch = 2 * hd + 16;
     p.stg_warp_bytes = (32 * p.stg_pitch + 127) / 128 * 128;
+    p.chunk_bytes = (2 * hd) % 16 == 0 ? 16 : 8;              // hd % 4 == 0, so a slice is at least 8-byte aligned
+    p.chunks_per_row = 2 * hd / p.chunk_bytes;
+    p.rows_per_iter = 32 / p.chunks_per_row;
     CUtensorMap mh, ml;
     if (int rc = make_plane_map(&mh, pl.hi, pl.rows_cap, hds, hdp, temporal != 0, J, F, S, p.G, L, p.Lp)) return rc;
     if (int rc = make_plane_map(&ml, pl.lo, pl.rows_cap, hds, hdp, temporal != 0, J, F, S, p.G, L, p.Lp)) return rc;
     // the group lengths of the H3WB parts get compile-time masks; anything else runs the generic instance
 #define PAFUSE_ATT_CASE(HDPV, LV)                                                             \
-    if (hdp == HDPV && (LV == 0 || L == LV)) {                                                \
-        constexpr int SP = HDPV == 32 ? 2 : 1;                                                \
-        if (split) return sep ? launch_tc<HDPV, LV, true, 2, SP>(mh, ml, p, st, sms)           \
-                              : launch_tc<HDPV, LV, false, 2, SP>(mh, ml, p, st, sms);        \
-        return sep ? launch_tc<HDPV, LV, true, 2, 1>(mh, ml, p, st, sms)                       \
-                   : (three ? launch_tc<HDPV, LV, false, (HDPV == 32 ? 3 : 2), 1>(mh, ml, p, st, sms) \
-                            : launch_tc<HDPV, LV, false, 2, 1>(mh, ml, p, st, sms));           \
-    }
+    if (hdp == HDPV && (LV == 0 || L == LV))                                                  \
+        return sep ? launch_tc<HDPV, LV, true, 2>(mh, ml, p, st, sms)                          \
+                   : (three ? launch_tc<HDPV, LV, false, (HDPV == 32 ? 3 : 2)>(mh, ml, p, st, sms) \
+                            : launch_tc<HDPV, LV, false, 2>(mh, ml, p, st, sms));
     PAFUSE_ATT_CASE(64, 24)
     PAFUSE_ATT_CASE(64, 27)
     PAFUSE_ATT_CASE(64, 0)

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -1123,6 +1124,23 @@ int pafuse_profile_read(pafuse_ctx* ctx, double* ms, double* work, int64_t* laun
         ms[r.cat] += (double)t;
         work[r.cat] += r.work;
         launches[r.cat] += 1;
+    }
+    // PAFUSE_PROF_DETAIL=1: the same launches grouped by (category, algorithmic work, bytes) -- one line per kernel kind
+    // and part, timed INSIDE the step (the ncu launch lists time every kernel alone, at another clock)
+    if (getenv("PAFUSE_PROF_DETAIL")) {
+        static const char* names[CAT_COUNT] = {"gemm", "attention", "layernorm", "embed_head", "ddim", "post"};
+        std::map<std::tuple<int, double, double>, std::pair<double, long long>> groups;
+        for (ProfRec& r : pr.recs) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, r.a, r.b);
+            auto& g = groups[std::make_tuple(r.cat, r.work, r.bytes)];
+            g.first += (double)t;
+            g.second += 1;
+        }
+        for (auto& kv : groups)
+            fprintf(stderr, "prof_detail %-10s work %.4e bytes %.4e launches %6lld avg_us %9.1f total_ms %9.2f\n", names[std::get<0>(kv.first)],
+                    std::get<1>(kv.first), std::get<2>(kv.first), kv.second.second, kv.second.first / (double)kv.second.second * 1e3,
+                    kv.second.first);
     }
     return 0;
 }
