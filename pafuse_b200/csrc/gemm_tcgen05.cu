@@ -150,6 +150,25 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t r[8]
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait_all() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#ifdef PAFUSE_GEMM_TRACE
+__device__ long long g_gemm_tr_bulk;   // measurement builds only: cycles lane 0 of the first epilogue warp of CTA 0 waits for its staging box
+#define GEMM_BULK_WAIT_READ()                                                                  \
+    {                                                                                          \
+        const long long t_bw = clock64();                                                      \
+        bulk_wait_group_read<0>();                                                             \
+        if (blockIdx.x == 0 && (threadIdx.x >> 5) == 4) g_gemm_tr_bulk += clock64() - t_bw;    \
+    }
+__device__ long long g_gemm_tr_ln[16];  // LayerNorm epilogue phases of the same warp: pass 1, merge 1, pass 2, merge 2, pass 3
+#define LN_TR(i)                                                                               \
+    if (blockIdx.x == 0 && threadIdx.x == 4 * 32) {                                            \
+        const long long t_now = clock64();                                                     \
+        g_gemm_tr_ln[i] += t_now - ln_t_last;                                                  \
+        ln_t_last = t_now;                                                                     \
+    }
+#else
+#define GEMM_BULK_WAIT_READ() bulk_wait_group_read<0>()
+#define LN_TR(i)
+#endif
 // the EPI_SUBS warps that share a TMEM lane quarter (128 threads), barrier id 1 + quarter
 __device__ __forceinline__ void quarter_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(EPI_SUBS * 32) : "memory"); }
 // staging-box offsets of 16-byte piece i of row `row`: fp32 boxes are 32 rows x 64 B with the 64-byte swizzle
@@ -189,6 +208,9 @@ __device__ __forceinline__ void stage_split16(uint32_t box_s, int lane, const fl
 // produces the values (shifted sums, see merge_stats).  x is fetched with coalesced 16-byte loads one chunk ahead
 // (registers), transposed through the warp's staging box, which then carries the output row by row to the TMA store.
 // coalesced fetch of a 32 x 16 box of x: lane -> 16 bytes at column (lane & 3) * 4 of rows (lane >> 2) + 8 i
+// x of one 16-column chunk, loaded coalesced (four lanes per row) and transposed through the staging box by the caller.
+// (Thread = row loads of the lane's own 64 bytes, without the transposition, measured SLOWER: the 32-line loads congest
+// the LSU and every other pass of the epilogue pays for it -- GEMM time per step 805 -> 829 ms, profiles/r2ag_*.)
 __device__ __forceinline__ void ln_fetch_x(const KernelParams& p, float4 (&xr)[4], int row0, int c0, int lane) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -266,6 +288,9 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         rstd = 1.0f / sqrtf(m2_acc * invN + eps);
     };
 
+#ifdef PAFUSE_GEMM_TRACE
+    long long ln_t_last = clock64();
+#endif
     // ---- pass 1: v = x + acc * scale + bias -> tensor memory (and, when not chained, -> x)
     // (all row arithmetic on packed pairs: FFMA2 / FADD2, see common.cuh)
     const float2 osc2 = splat2(oscale);
@@ -277,7 +302,7 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         float4 bv[4];
         tmem_ld_32x16(t_base + (uint32_t)c0, r);
         load_vec16(bv, p.bias + c0);
-        if (lane == 0) bulk_wait_group_read<0>();                     // the store that last used the box has read it
+        if (lane == 0) GEMM_BULK_WAIT_READ();                     // the store that last used the box has read it
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i)                                   // transpose x through the box
@@ -313,8 +338,10 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         }
     }
     tmem_st_wait_all();
+    LN_TR(0)
     float mean, rstd;
     merge_stats(K, S2.x + S2.y, Q2.x + Q2.y, chained ? f.eps0 : f.eps1, mean, rstd);
+    LN_TR(1)
 
     if (chained) {
         // ---- y = LN(v; g0, b0) [+ add_f[f]] -> x and tensor memory
@@ -344,7 +371,7 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
                     y[2 * i + 1] = fadd2(y[2 * i + 1], make_float2(a.z, a.w));
                 }
             }
-            if (lane == 0) bulk_wait_group_read<0>();
+            if (lane == 0) GEMM_BULK_WAIT_READ();
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -368,7 +395,9 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
             }
         }
         tmem_st_wait_all();
+        LN_TR(2)
         merge_stats(K, S2.x + S2.y, Q2.x + Q2.y, f.eps1, mean, rstd);
+        LN_TR(3)
     }
 
     // ---- a = LN(row values in tensor memory; g1, b1) -> fp16 hi/lo boxes -> TMA stores
@@ -388,7 +417,7 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
                 v[2 * i] = ffma2(ffma2(pair_of(r, 2 * i), rstd2, mr2), make_float2(gv[i].x, gv[i].y), make_float2(bv[i].x, bv[i].y));
                 v[2 * i + 1] = ffma2(ffma2(pair_of(r, 2 * i + 1), rstd2, mr2), make_float2(gv[i].z, gv[i].w), make_float2(bv[i].z, bv[i].w));
             }
-            if (lane == 0) bulk_wait_group_read<0>();                 // the store that last used the box has read it
+            if (lane == 0) GEMM_BULK_WAIT_READ();                 // the store that last used the box has read it
             __syncwarp();
             stage_split16(box_s, lane, v);
             fence_proxy_async_smem();
@@ -401,6 +430,7 @@ __device__ __forceinline__ void epilogue_resid_ln(const KernelParams& p, const C
         }
     }
 
+    LN_TR(4)
     // the accumulator buffer goes back to the MMA issuer
     tcgen05_fence_before();
     __syncwarp();
@@ -618,6 +648,17 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 else mbar_arrive_cluster(bar, 0);
             }
         };
+#ifdef PAFUSE_GEMM_TRACE
+        // measurement builds only: cycles this epilogue warp waits for an accumulator vs. works on it, per tile
+        long long tr_wait = 0, tr_work = 0, tr_last = clock64();
+        if (blockIdx.x == 0 && threadIdx.x == 4 * 32) {
+            g_gemm_tr_bulk = 0;
+            for (int i = 0; i < 16; ++i) g_gemm_tr_ln[i] = 0;
+        }
+#define GEMM_TR(acc) { const long long t_now = clock64(); acc += t_now - tr_last; tr_last = t_now; }
+#else
+#define GEMM_TR(acc)
+#endif
         for (int it = 0; it < walk.count; ++it) {
             int m_tile, n_tile;
             walk.at(it, m_tile, n_tile);
@@ -636,8 +677,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             if (EPI == EPI_RESID_LN) {
                 if (sub < nck) ln_fetch_x(p, xr, row0, sub * CW, lane);   // in flight while the main loop finishes
             }
+            GEMM_TR(tr_work)
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tcgen05_fence_after();
+            GEMM_TR(tr_wait)
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
             if (EPI == EPI_RESID_LN) {
                 epilogue_resid_ln<CG>(p, tm_out0, tm_out1, tm_out2, box, ln_xch, t_base, row0, q, sub, lane, BN, oscale,
@@ -654,7 +697,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                 const int col = n_tile * BN + c0;
                 float4 bv[4];
                 load_vec16(bv, p.bias + col);
-                if (lane == 0) bulk_wait_group_read<0>();             // the store that last used the box has read it
+                if (lane == 0) GEMM_BULK_WAIT_READ();             // the store that last used the box has read it
                 tmem_ld_wait();
                 if (c + EPI_SUBS >= nck) release(&tmem_empty_bar[acc]);
                 __syncwarp();
@@ -701,6 +744,14 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        GEMM_TR(tr_work)
+#ifdef PAFUSE_GEMM_TRACE
+        if (blockIdx.x == 0 && lane == 0 && q == 0 && sub == 0 && walk.count > 0)
+            printf("gemm_trace EPI=%d WRES=%d N=%d K=%d tiles=%d cycles/tile: wait_tmem_full %lld | epilogue_work %lld | of_which_staging_box_wait %lld | LN pass1 %lld merge1 %lld pass2 %lld merge2 %lld pass3 %lld\n", EPI,
+                   (int)WRES, p.N, p.K, walk.count, tr_wait / walk.count, tr_work / walk.count, g_gemm_tr_bulk / walk.count,
+                   g_gemm_tr_ln[0] / walk.count, g_gemm_tr_ln[1] / walk.count, g_gemm_tr_ln[2] / walk.count, g_gemm_tr_ln[3] / walk.count,
+                   g_gemm_tr_ln[4] / walk.count);
+#endif
         if (lane == 0) bulk_wait_group<0>();                          // all output boxes are written before the CTA retires
     }
 
