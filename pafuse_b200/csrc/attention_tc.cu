@@ -513,13 +513,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         };
 
         // ---- O of unit `it` / sum -> fp16 hi/lo -> global
-        auto output_unit = [&](int it, float sum) {
+        // o_seen: the caller has already waited for this unit's o_full phase (separate layout, inside softmax_unit of the
+        // unit two later).  Waiting a second time on the same parity would only be safe while PV of the NEXT unit has
+        // not completed yet: once it has, that parity names the phase in progress and the wait never returns.
+        auto output_unit = [&](int it, float sum, bool o_seen) {
             const int n_use = it / NSTG, ob = p.o_bufs == 2 ? n_use & 1 : 0;
             const uint32_t ph = (uint32_t)(p.o_bufs == 2 ? n_use >> 1 : n_use) & 1u;
             const uint32_t ob_off = (uint32_t)(ob * HDP);
             const int u = (int)blockIdx.x + it * (int)gridDim.x;
             const int tile = u >> 3, head = u & 7;
-            mbar_wait(&o_full[wg * 2 + ob], ph);
+            if (!o_seen) mbar_wait(&o_full[wg * 2 + ob], ph);
             tcgen05_fence_after();
             ATT_TR(6)
 #ifdef PAFUSE_ABLATE
@@ -642,7 +645,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         } else if (!SEP && p.o_bufs != 2) {
             for (int it = wg; it < n_local; it += NSTG) {
                 const float sum = softmax_unit(it);
-                output_unit(it, sum);
+                output_unit(it, sum, false);
             }
         } else {
             // software pipeline: the output of unit it-2 (its PV ran during the softmax of unit it) follows the
@@ -653,11 +656,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             int prev = -1;
             for (int it = wg; it < n_local; it += NSTG) {
                 const float sum = softmax_unit(it);
-                if (prev >= 0) output_unit(prev, prev_sum);
+                if (prev >= 0) output_unit(prev, prev_sum, SEP);   // SEP: softmax_unit(it) waited for o_full of unit it - NSTG = prev
                 prev = it;
                 prev_sum = sum;
             }
-            if (prev >= 0) output_unit(prev, prev_sum);
+            if (prev >= 0) output_unit(prev, prev_sum, false);
         }
 #ifdef PAFUSE_ATT_TRACE
         if (blockIdx.x == 0 && lane == 0 && q == 0 && n_local > 0)
