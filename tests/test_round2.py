@@ -255,3 +255,20 @@ def test_reassembly_tables_are_cached_and_follow_a_changed_dataset():
     face = ds.parts_joint_indices["face"]
     assert not torch.equal(a[:, face], c[:, face])
     assert torch.equal(pafuse_b200.wb_pose_from_parts(x.clone(), ds), a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("switch", ["PAFUSE_ATT_PIPE=0", "PAFUSE_ATT_STAGES=3", "PAFUSE_ATT_SEP=0"])
+def test_opt_in_attention_variants_stay_parity_green(switch):
+    """The attention switches are read once per process, so every variant runs the attention parity cases in a child
+    process: the order without the second output buffer, three units in flight, aliased layout only."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    name, value = switch.split("=")
+    env = dict(os.environ, **{name: value})
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "test_attention or test_qkv_gemm_head_plane_epilogue_feeds_attention", "-p", "no:cacheprovider"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-500:]
