@@ -344,7 +344,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
                 // O buffer of this unit and its use count: with two buffers per stage, uses alternate between them
                 const int n_use = it / NSTG, ob = p.o_bufs == 2 ? n_use & 1 : 0;
                 const uint32_t ph_o = (uint32_t)(p.o_bufs == 2 ? n_use >> 1 : n_use) & 1u;
-                const uint32_t ob_off = (uint32_t)(ob * HDP);
+                const uint32_t ob_off = (uint32_t)(ob * p.n_acc * HDP);
                 mbar_wait(&o_empty[stage * 2 + ob], ph_o ^ 1); // the softmax group has read what PV last wrote into this buffer
                 mbar_wait(&p_full[stage], ph);                 // P of this unit is in tensor memory
                 tcgen05_fence_after();
@@ -519,7 +519,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         auto output_unit = [&](int it, float sum, bool o_seen) {
             const int n_use = it / NSTG, ob = p.o_bufs == 2 ? n_use & 1 : 0;
             const uint32_t ph = (uint32_t)(p.o_bufs == 2 ? n_use >> 1 : n_use) & 1u;
-            const uint32_t ob_off = (uint32_t)(ob * HDP);
+            const uint32_t ob_off = (uint32_t)(ob * p.n_acc * HDP);
             const int u = (int)blockIdx.x + it * (int)gridDim.x;
             const int tile = u >> 3, head = u & 7;
             if (!o_seen) mbar_wait(&o_full[wg * 2 + ob], ph);
@@ -826,8 +826,13 @@ int launch_attention_tc(const AttnPlanes& pl, op_t* o_hi, op_t* o_lo, int S, int
         }
     }
     if (p.n_acc > g_n_acc_cap) p.n_acc = g_n_acc_cap < 1 ? 1 : g_n_acc_cap;
-    // aliased layout, two stages, one accumulator per unit: the stage's O columns hold TWO buffers (the stride above is >= 2 * hdp)
-    p.o_bufs = (!sep && !three && p.n_acc == 1 && g_pipe_o) ? 2 : 1;
+    // aliased layout, two stages: the 256 columns behind the S / P regions hold TWO O buffers per stage of n_acc accumulators
+    // each, when they fit (one accumulator for the wide heads, up to two for the narrow ones)
+    p.o_bufs = 1;
+    if (!sep && !three && g_pipe_o && 2 * 2 * p.n_acc * hdp <= 256) {
+        p.o_bufs = 2;
+        p.tm_stride_o = 2 * p.n_acc * hdp;
+    }
 #ifdef PAFUSE_ABLATE
     p.ablate = getenv("PAFUSE_ABLATE") ? atoi(getenv("PAFUSE_ABLATE")) : 0;
 #endif

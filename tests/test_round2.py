@@ -258,10 +258,10 @@ def test_reassembly_tables_are_cached_and_follow_a_changed_dataset():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("switch", ["PAFUSE_ATT_PIPE=0", "PAFUSE_ATT_STAGES=3", "PAFUSE_ATT_SEP=0"])
+@pytest.mark.parametrize("switch", ["PAFUSE_ATT_PIPE=0", "PAFUSE_ATT_STAGES=3", "PAFUSE_ATT_SEP=0", "PAFUSE_ATT_NACC=2"])
 def test_opt_in_attention_variants_stay_parity_green(switch):
     """The attention switches are read once per process, so every variant runs the attention parity cases in a child
-    process: the order without the second output buffer, three units in flight, aliased layout only."""
+    process: the order without the second output buffer, three units in flight, aliased layout only, two PV accumulators."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
